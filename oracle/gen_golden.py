@@ -1,0 +1,223 @@
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (read-only at /root/reference).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the GPU box has no reference):
+
+    python -m oracle.gen_golden
+
+What is recorded (all seeds fixed, sizes tiny so the fixtures stay small):
+  scan_*.npz  : inputs, ``selective_scan_ref`` output / last_state
+                (nnunetv2/nets/seg_mamba/selective_scan_interface.py:86-152, verbatim), and the
+                gradients torch.autograd produces through it for a random upstream gradient.
+  cross_*.npz : what the reference's own ``SS2D.forward_core`` (m2net.py:170-206, sum :218) and
+                ``SSND.forward_core`` (ssnd2net.py:239-302) feed to / make from the scan, captured by
+                swapping ``self.selective_scan`` for a recorder that returns a fixed random out_y.
+  module_*.npz: state_dict + input + output + input/parameter gradients of reference
+                SS2D (m2net.py:39-225) and SSND 2-D / 3-D (ssnd2net.py:73-318) modules, with the
+                reference's selective_scan_ref as the scan.
+  MANIFEST.json: case list plus the agreement of oracle/torch_port.py and oracle/scan_oracle.c with
+                the verbatim reference at generation time.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import cross_oracle, ref_loader, scan_oracle, torch_port
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+# name: (batch, dim, groups (0 = 3-D B/C), dstate, L, has_D, has_z, has_bias, softplus, io dtype)
+SCAN_CASES = {
+    "scan_base_g2":       (2, 8, 2, 16, 64, True, False, True, True, "float32"),
+    "scan_z_3d_L75":      (2, 6, 0, 16, 75, True, True, True, True, "float32"),
+    "scan_plain_g4_L33":  (1, 4, 4, 16, 33, False, False, False, False, "float32"),
+    "scan_long_z_L1100":  (1, 4, 1, 16, 1100, True, True, True, True, "float32"),
+    "scan_bf16_z_L128":   (2, 8, 1, 16, 128, True, True, True, True, "bfloat16"),
+    "scan_fp16_L96":      (1, 8, 2, 16, 96, True, False, True, True, "float16"),
+    "scan_n8_L40":        (1, 4, 1, 8, 40, True, False, True, True, "float32"),
+}
+
+
+def make_scan_inputs(name, seed):
+    bsz, dim, groups, n, L, has_D, has_z, has_bias, softplus, dt = SCAN_CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    dtype = getattr(torch, dt)
+    u = torch.randn(bsz, dim, L, generator=g).to(dtype)
+    if softplus:
+        delta = (0.5 * torch.randn(bsz, dim, L, generator=g)).to(dtype)
+    else:
+        delta = (0.001 + 0.1 * torch.rand(bsz, dim, L, generator=g)).to(dtype)
+    # S4D-real init (m2net.py:144-149) with a trainable-style jitter so rows differ
+    A = -(torch.arange(1, n + 1).float().repeat(dim, 1) * torch.exp(0.1 * torch.randn(dim, n, generator=g)))
+    bshape = (bsz, n, L) if groups == 0 else (bsz, groups, n, L)
+    B = torch.randn(*bshape, generator=g).to(dtype)
+    C = torch.randn(*bshape, generator=g).to(dtype)
+    D = (1.0 + 0.1 * torch.randn(dim, generator=g)) if has_D else None
+    z = torch.randn(bsz, dim, L, generator=g).to(dtype) if has_z else None
+    if has_bias:
+        # inverse-softplus of log-uniform dt in [1e-3, 1e-1] (m2net.py:128-135)
+        dtv = torch.exp(torch.rand(dim, generator=g) * (np.log(0.1) - np.log(0.001)) + np.log(0.001))
+        bias = dtv + torch.log(-torch.expm1(-dtv))
+    else:
+        bias = None
+    gout = torch.randn(bsz, dim, L, generator=g).to(dtype)
+    return dict(u=u, delta=delta, A=A, B=B, C=C, D=D, z=z, delta_bias=bias, gout=gout), softplus
+
+
+def _np(t):
+    if t is None:
+        return None
+    t = t.detach()
+    if t.dtype in (torch.bfloat16, torch.float16):
+        # store 16-bit payloads losslessly as their fp32 images
+        return t.float().numpy()
+    return t.numpy()
+
+
+def gen_scan(manifest):
+    ref = ref_loader.selective_scan_ref()
+    for seed, name in enumerate(SCAN_CASES):
+        inp, softplus = make_scan_inputs(name, 1000 + seed)
+        leaves = {k: (v.clone().requires_grad_(True) if v is not None and k != "gout" else v)
+                  for k, v in inp.items()}
+        out, last = ref(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"],
+                        leaves["D"], leaves["z"], leaves["delta_bias"], softplus, True)
+        out.backward(inp["gout"])
+        rec = {f"in_{k}": _np(v) for k, v in inp.items() if v is not None}
+        rec["out"] = _np(out)
+        rec["last_state"] = _np(last)
+        for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias"):
+            if leaves[k] is not None:
+                rec[f"grad_{k}"] = _np(leaves[k].grad)
+        rec["meta_softplus"] = np.array(int(softplus))
+        rec["meta_dtype"] = np.array(SCAN_CASES[name][-1])
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+
+        # agreement of the two restatements with the verbatim reference, recorded for the record
+        with torch.no_grad():
+            port = torch_port.selective_scan_port(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"],
+                                                  inp["D"], inp["z"], inp["delta_bias"], softplus)
+        c_out = scan_oracle.selective_scan_oracle(inp["u"], inp["delta"], inp["A"], inp["B"], inp["C"],
+                                                  inp["D"], inp["z"], inp["delta_bias"], softplus)
+        manifest["scan"][name] = dict(
+            shape=SCAN_CASES[name][:5], dtype=SCAN_CASES[name][-1],
+            torch_port_max_abs_diff=float((port.float() - out.float()).abs().max()),
+            c_oracle_max_abs_diff=float(np.abs(c_out - _np(out)).max()),
+            out_abs_max=float(out.float().abs().max()))
+
+
+class _Recorder:
+    """Stands in for ``self.selective_scan``: records xs, returns a fixed random out_y."""
+
+    def __init__(self, seed):
+        self.seed = seed
+        self.xs = None
+        self.out_y = None
+
+    def __call__(self, xs, dts, As, Bs, Cs, Ds, z=None, delta_bias=None, delta_softplus=None,
+                 return_last_state=None):
+        self.xs = xs.detach().clone()
+        g = torch.Generator().manual_seed(self.seed)
+        self.out_y = torch.randn(xs.shape, generator=g)
+        return self.out_y.clone()
+
+
+def gen_cross(manifest):
+    m2 = ref_loader.m2net()
+    sn = ref_loader.ssnd2net()
+    torch.manual_seed(7)
+    # ---- 2-D through m2net.SS2D.forward_core (:170-206) and the :218 sum ----
+    for name, (bsz, H, W, dm) in {"cross_2d_a": (2, 4, 6, 4), "cross_2d_sq": (1, 8, 8, 2),
+                                  "cross_2d_odd": (1, 3, 5, 2)}.items():
+        mod = m2.SS2D(d_model=dm).eval()
+        rec = _Recorder(11)
+        mod.selective_scan = rec
+        x = torch.randn(bsz, mod.d_inner, H, W)
+        with torch.no_grad():
+            y1, y2, y3, y4 = mod.forward_core(x)
+            y = y1 + y2 + y3 + y4                                    # m2net.py:218
+        K = 4
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), x=_np(x),
+                            xs=_np(rec.xs.view(bsz, K, -1, H * W)),
+                            out_y=_np(rec.out_y.view(bsz, K, -1, H * W)), y=_np(y))
+        ours_xs = cross_oracle.cross_scan_2d(_np(x))
+        ours_y = cross_oracle.cross_merge_2d(_np(rec.out_y.view(bsz, K, -1, H * W)), H, W)
+        manifest["cross"][name] = dict(shape=[bsz, mod.d_inner, H, W],
+                                       oracle_scan_equal=bool(np.array_equal(ours_xs, _np(rec.xs.view(bsz, K, -1, H * W)))),
+                                       oracle_merge_equal=bool(np.array_equal(ours_y, _np(y))))
+    # ---- 2-D and 3-D through ssnd2net.SSND.forward_core (:239-302) ----
+    for name, (sd, bsz, dims, dm) in {"cross_ssnd2d": (2, 1, (3, 4), 2),
+                                      "cross_3d_a": (3, 1, (2, 3, 5), 2),
+                                      "cross_3d_b": (3, 2, (4, 2, 3), 2)}.items():
+        mod = sn.SSND(spatial_dims=sd, factorization_type="cross-scan", d_model=dm).eval()
+        rec = _Recorder(13)
+        mod.selective_scan = rec
+        x = torch.randn(bsz, mod.d_inner, *dims)
+        with torch.no_grad():
+            y = mod.forward_core(x)          # (B, *dims, D)
+        K = mod.k
+        L = int(np.prod(dims))
+        y_bdl = y.reshape(bsz, L, -1).transpose(1, 2).contiguous()   # undo :284 / :299 transpose
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), x=_np(x),
+                            xs=_np(rec.xs.view(bsz, K, -1, L)), out_y=_np(rec.out_y.view(bsz, K, -1, L)),
+                            y=_np(y_bdl), dims=np.array(dims))
+        if sd == 2:
+            ours_xs = cross_oracle.cross_scan_2d(_np(x))
+            ours_y = cross_oracle.cross_merge_2d(_np(rec.out_y.view(bsz, K, -1, L)), *dims)
+        else:
+            ours_xs = cross_oracle.cross_scan_3d(_np(x))
+            ours_y = cross_oracle.cross_merge_3d(_np(rec.out_y.view(bsz, K, -1, L)), *dims)
+        manifest["cross"][name] = dict(shape=[bsz, mod.d_inner, *dims],
+                                       oracle_scan_equal=bool(np.array_equal(ours_xs, _np(rec.xs.view(bsz, K, -1, L)))),
+                                       oracle_merge_equal=bool(np.array_equal(ours_y, _np(y_bdl))))
+
+
+def gen_module(manifest):
+    m2 = ref_loader.m2net()
+    sn = ref_loader.ssnd2net()
+    specs = {
+        "module_ss2d_m8": (lambda: m2.SS2D(d_model=8), (2, 6, 5, 8)),
+        "module_ss2d_m32": (lambda: m2.SS2D(d_model=32), (1, 8, 8, 32)),
+        "module_ssnd2d_m8": (lambda: sn.SSND(spatial_dims=2, factorization_type="cross-scan", d_model=8), (1, 4, 6, 8)),
+        "module_ssnd3d_m8": (lambda: sn.SSND(spatial_dims=3, factorization_type="cross-scan", d_model=8), (1, 2, 3, 5, 8)),
+    }
+    for i, (name, (ctor, xshape)) in enumerate(specs.items()):
+        torch.manual_seed(100 + i)
+        mod = ctor().eval()
+        # move the trainable scan parameters off their symmetric init so every direction differs
+        with torch.no_grad():
+            mod.A_logs.add_(0.1 * torch.randn_like(mod.A_logs))
+            mod.Ds.add_(0.1 * torch.randn_like(mod.Ds))
+        x = torch.randn(*xshape, requires_grad=True)
+        y = mod(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        rec = {"x": _np(x), "y": _np(y), "gy": _np(gy), "gx": _np(x.grad)}
+        for k, v in mod.state_dict().items():
+            rec["sd_" + k] = _np(v)
+        for k, p in mod.named_parameters():
+            rec["gp_" + k] = _np(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+        manifest["module"][name] = dict(x_shape=list(xshape), y_abs_mean=float(y.abs().mean()))
+
+
+def main():
+    assert ref_loader.available(), "run in the build container: /root/reference is required"
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    manifest = {"generator": "python -m oracle.gen_golden", "torch": torch.__version__,
+                "reference": "AI-in-Cardiovascular-Medicine/nnUZoo @ /root/reference (read-only mount)",
+                "scan": {}, "cross": {}, "module": {}}
+    gen_scan(manifest)
+    gen_cross(manifest)
+    gen_module(manifest)
+    with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+    print(json.dumps(manifest, indent=1, sort_keys=True))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,178 @@
+"""Load pieces of the read-only reference (/root/reference) on the CPU -- TEST INFRASTRUCTURE ONLY.
+
+Used by oracle/gen_golden.py (to make tests/golden/) and by container-only tests that are skipped
+when /root/reference is absent (it never exists on the GPU box).  Nothing here is imported by the
+product package.
+
+The reference's model files import third-party packages that are not installed in this image
+(mamba_ssm, monai, timm, dynamic_network_architectures, ...).  We satisfy those imports with empty
+stub modules, give real behaviour only to the handful of symbols the SS2D / SSND modules actually
+execute (DropPath, trunc_normal_, monai's conv-only Convolution), and bind
+``mamba_ssm.ops.selective_scan_interface.selective_scan_fn`` to the reference's own pure-PyTorch
+``selective_scan_ref`` so that the reference modules run their own arithmetic end to end
+(recipe: SURVEY.md appendix).
+"""
+from __future__ import annotations
+
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import os
+import sys
+import types
+import warnings
+
+REF_ROOT = os.environ.get("NNUZOO_REFERENCE_ROOT", "/root/reference")
+_STUB_ROOTS = ("mamba_ssm", "monai", "timm", "dynamic_network_architectures", "batchgenerators",
+               "batchgeneratorsv2", "acvl_utils", "torchinfo", "nnunetv2", "causal_conv1d",
+               "causal_conv1d_cuda", "selective_scan_cuda", "prettytable", "deep_utils")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_ROOT, "nnunetv2", "nets"))
+
+
+class _Anything:
+    """Placeholder for any attribute of a stubbed package (usable in annotations like ``A | str``)."""
+
+    def __init__(self, name="stub"):
+        self._name = name
+
+    def __call__(self, *a, **k):
+        raise RuntimeError(f"stubbed third-party symbol {self._name} was actually called")
+
+    def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        return _Anything(f"{self._name}.{item}")
+
+    def __or__(self, other):
+        return self
+
+    __ror__ = __or__
+
+    def __mro_entries__(self, bases):  # allow ``class X(stub):``
+        return (object,)
+
+
+class _StubModule(types.ModuleType):
+    __path__: list = []
+
+    def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        return _Anything(f"{self.__name__}.{item}")
+
+
+class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] in _STUB_ROOTS:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _StubModule(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+_installed = False
+_cache: dict = {}
+
+
+def _install_stubs():
+    global _installed
+    if _installed:
+        return
+    import torch
+    import torch.nn as nn
+
+    sys.meta_path.insert(0, _StubFinder())
+    _installed = True
+
+    # --- timm.layers: the two symbols SS2D-family files execute ---------------------------------
+    import timm.layers as tl  # noqa: E402  (stub)
+
+    class DropPath(nn.Module):  # stochastic depth; identity in eval() and at drop_prob 0
+        def __init__(self, drop_prob: float = 0.0, scale_by_keep: bool = True):
+            super().__init__()
+            self.drop_prob, self.scale_by_keep = drop_prob, scale_by_keep
+
+        def forward(self, x):
+            if self.drop_prob == 0.0 or not self.training:
+                return x
+            keep = 1 - self.drop_prob
+            mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+            if keep > 0.0 and self.scale_by_keep:
+                mask.div_(keep)
+            return x * mask
+
+    tl.DropPath = DropPath
+    tl.trunc_normal_ = lambda t, std=1.0, **kw: nn.init.trunc_normal_(t, std=std, **kw)
+
+    # --- monai conv-only Convolution (ssnd2net.py:110-120): Sequential with one "conv" child ------
+    import monai.networks.blocks as mb  # noqa: E402  (stub)
+
+    class Convolution(nn.Sequential):
+        def __init__(self, spatial_dims, in_channels, out_channels, strides=1, kernel_size=3,
+                     groups=1, bias=True, conv_only=False, dilation=1, padding=None, **kw):
+            super().__init__()
+            assert conv_only, "only the conv_only form is stood in for"
+            conv_t = {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}[spatial_dims]
+            self.add_module("conv", conv_t(in_channels, out_channels, kernel_size, stride=strides,
+                                           padding=padding, dilation=dilation, groups=groups, bias=bias))
+
+    mb.Convolution = Convolution
+    import monai.networks.blocks.convolutions as mbc  # noqa: E402
+
+    mbc.Convolution = Convolution
+
+    import dynamic_network_architectures.initialization.weight_init as wi  # noqa: E402
+
+    wi.init_last_bn_before_add_to_0 = lambda m: None
+
+    # --- the scan itself: the reference's own pure-PyTorch statement -----------------------------
+    ssi = load_file("ref_selective_scan_interface",
+                    "nnunetv2/nets/seg_mamba/selective_scan_interface.py")
+    import mamba_ssm.ops.selective_scan_interface as mssi  # noqa: E402  (stub)
+
+    mssi.selective_scan_fn = ssi.selective_scan_ref
+    mssi.selective_scan_ref = ssi.selective_scan_ref
+    _ = torch
+
+
+def load_file(modname: str, relpath: str):
+    """Import one reference source file by path under a private module name."""
+    if modname in _cache:
+        return _cache[modname]
+    if not available():
+        raise FileNotFoundError(f"reference not mounted at {REF_ROOT}")
+    if modname != "ref_selective_scan_interface":
+        _install_stubs()
+    else:
+        for m in ("causal_conv1d", "causal_conv1d_cuda", "selective_scan_cuda"):
+            if m not in sys.modules:
+                sys.modules[m] = types.ModuleType(m)
+                sys.modules[m].causal_conv1d_fn = None
+    spec = importlib.util.spec_from_file_location(modname, os.path.join(REF_ROOT, relpath))
+    mod = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    _cache[modname] = mod
+    return mod
+
+
+def selective_scan_ref():
+    """The reference's oracle, selective_scan_interface.py:86-152, verbatim."""
+    return load_file("ref_selective_scan_interface",
+                     "nnunetv2/nets/seg_mamba/selective_scan_interface.py").selective_scan_ref
+
+
+def m2net():
+    return load_file("ref_m2net", "nnunetv2/nets/m2net.py")
+
+
+def ssnd2net():
+    return load_file("ref_ssnd2net", "nnunetv2/nets/ssnd2net.py")
