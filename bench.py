@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of BASELINE.json measured on B200.
+
+One "step" = one pass of the hot path over one batch: the 80 SS2D selective scans (forward AND
+backward, fp32 scan I/O as the reference's SS2D forces at m2net.py:185-191) of one SS2D2Net/M2Net
+training step at BASELINE configs[1]: batch 12 x 1x512x512 (scan list: SURVEY.md section 8a).
+
+  value      whole-job GB/s, algorithmic bytes of the selective_scan_fn boundary, 4*(8E + 6S) per
+             fwd+bwd scan, inputs resident in HBM; every scan reads a fresh slice of
+             >1 GB operand buffers, so nothing is L2-warm ("inputs larger than L2").
+  e2e        the same metric through the host-buffer C-ABI call nz_scan_fwd_bwd_host: pinned host
+             operands in, all results back to the host, copies inside the timed region.
+  roofline   all launches of the dominant kernel (scan_bwd) inside the timed region, CUDA events on
+             the launching stream, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference
+             the reference's CPU path (selective_scan_ref restated in oracle/torch_port.py; the
+             reference itself is not on the GPU box) on a bounded sample of the same workload.
+
+Multi-GPU (torchrun, one rank per GPU): the scan has no cross-row dependency and the path has no
+exchange step, so every rank runs the full per-GPU batch (weak scaling, "replicas only", no
+collective on the data path); time is the max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_STATE = 16
+K_DIR = 4
+BATCH = 12
+
+
+def m2net_scan_list(res: int = 512):
+    """(K*D, L) of every selective_scan_fn call of one M2Net forward (m2net.py:810-872; MU stages
+    :646-655, :405-427, :461-474): stage s has mid channels 16*2^s (K*D = 8*mid), depth n = 7-s and
+    input resolution res/2^s; encoder scans L = r^2, (r/2)^2, ..., last one twice; decoder the same
+    without the duplicate; each stage appears twice (encoder side and decoder side of the U)."""
+    scans = []
+    for s in range(4):
+        kd = 8 * 16 * 2 ** s
+        n = 7 - s
+        r = res >> s
+        enc = [(r >> i) ** 2 for i in range(n - 1)]
+        enc.append(enc[-1])
+        dec = enc[:-1]
+        for _ in range(2):
+            scans += [(kd, L) for L in enc + dec]
+    return scans
+
+
+def scan_bytes(batch, kd, L, w=4):
+    E = batch * kd * L
+    S = batch * K_DIR * N_STATE * L
+    return dict(E=E, S=S, fwd=w * (3 * E + 2 * S), bwd=w * (5 * E + 4 * S), total=w * (8 * E + 6 * S))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].startswith("Active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own CPU path on a bounded sample of the workload
+# -------------------------------------------------------------------------------------------------
+def cpu_sample_run(steps: int, warmup: int):
+    """fwd+bwd of one workload scan at reduced size through the torch port of selective_scan_ref."""
+    import torch
+
+    from oracle.torch_port import selective_scan_port
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    batch, kd, L = 1, 128, 128 * 128  # the stage-1 (K*D = 128) scan of the workload at its 128x128 level
+    g = torch.Generator().manual_seed(0)
+    u = torch.randn(batch, kd, L, generator=g, requires_grad=True)
+    delta = (0.5 * torch.randn(batch, kd, L, generator=g)).requires_grad_(True)
+    A = (-torch.arange(1, N_STATE + 1).float().repeat(kd, 1)).requires_grad_(True)
+    B = torch.randn(batch, K_DIR, N_STATE, L, generator=g, requires_grad=True)
+    C = torch.randn(batch, K_DIR, N_STATE, L, generator=g, requires_grad=True)
+    D = torch.ones(kd, requires_grad=True)
+    bias = torch.full((kd,), -2.0, requires_grad=True)
+    gout = torch.randn(batch, kd, L, generator=g)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = selective_scan_port(u, delta, A, B, C, D, None, bias, True)
+        out.backward(gout)
+        times.append(time.perf_counter() - t0)
+        for t in (u, delta, A, B, C, D, bias):
+            t.grad = None
+    t = sum(times[warmup:]) / max(1, steps)
+    nbytes = scan_bytes(batch, kd, L)["total"]
+    return dict(seconds=t, gbps=nbytes / t / 1e9, cores=torch.get_num_threads(),
+                sample=f"selective_scan_ref port (oracle/torch_port.py) fwd+bwd, one stage-1 scan of the workload "
+                       f"at batch {batch}, K*D={kd}, L={L} fp32 ({nbytes / 1e6:.1f} MB algorithmic)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_sample_run(args.steps, 1)  # one CPU warm-up pass is enough; each pass takes seconds
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["gbps"], "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": 1, "ms_per_step": r["seconds"] * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": CONFIG,
+        "cpu_baseline": {"value": r["gbps"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["gbps"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+METRIC = "SS2D selective-scan fwd+bwd GB/s (selective_scan_fn boundary bytes 4*(8E+6S))"
+CONFIG = {"workload": "configs[1]: all 80 SS2D selective scans (fwd+bwd) of one SS2D2Net/M2Net training step, "
+                      "batch 12 x 1x512x512, fp32 scan I/O, d_state 16, K=4",
+          "scans_per_step": 80, "batch": BATCH, "l2": "inputs larger than L2 (each scan reads a fresh slice of "
+                                                      ">1 GB buffers)",
+          "parallelism": "replicas (one full batch per GPU, no data-path collective)"}
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------
+class Workload:
+    def __init__(self, dev):
+        import torch
+
+        from nnuzoo_b200 import _native
+        from nnuzoo_b200._native import NzScanDesc
+
+        self.torch, self.native, self.Desc = torch, _native, NzScanDesc
+        self.dev = dev
+        self.lib = _native.lib()
+        _native.bind_device(dev.index)
+        self.scans = m2net_scan_list(512)
+        kd_max_elems = max(BATCH * kd * L for kd, L in self.scans)
+        bc_max = max(BATCH * K_DIR * N_STATE * L for _, L in self.scans)
+        self.pool_mult = 2  # operand pools are 2x the largest scan so slices rotate
+        g = torch.Generator(device=dev).manual_seed(1234 + dev.index)
+        rnd = lambda n, scale=1.0: torch.randn(n, device=dev, generator=g) * scale  # noqa: E731
+        self.u = rnd(kd_max_elems * self.pool_mult)
+        self.delta = rnd(kd_max_elems * self.pool_mult, 0.5)
+        self.dout = rnd(kd_max_elems * self.pool_mult)
+        self.Bm = rnd(bc_max * self.pool_mult)
+        self.Cm = rnd(bc_max * self.pool_mult)
+        self.out = torch.empty(kd_max_elems, device=dev)
+        self.du = torch.empty(kd_max_elems, device=dev)
+        self.dd = torch.empty(kd_max_elems, device=dev)
+        self.dB = torch.empty(bc_max, device=dev)
+        self.dC = torch.empty(bc_max, device=dev)
+        kdm = max(kd for kd, _ in self.scans)
+        self.A = -torch.arange(1, N_STATE + 1, device=dev).float().repeat(kdm, 1).contiguous()
+        self.D = torch.ones(kdm, device=dev)
+        self.bias = torch.full((kdm,), -2.0, device=dev)
+        self.dA = torch.zeros(kdm, N_STATE, device=dev)
+        self.dD = torch.zeros(kdm, device=dev)
+        self.dbias = torch.zeros(kdm, device=dev)
+        nch_max = max(BATCH * kd * ((L + 255) // 256) * N_STATE for kd, L in self.scans)
+        self.x = torch.empty(nch_max, device=dev)
+        self.cur_row = 0
+        self.cur_bc = 0
+        self.total_bytes = sum(scan_bytes(BATCH, kd, L)["total"] for kd, L in self.scans)
+        self.bwd_bytes = sum(scan_bytes(BATCH, kd, L)["bwd"] for kd, L in self.scans)
+
+    def _slice(self, buf, cur, n):
+        if cur + n > buf.numel():
+            cur = 0
+        return buf[cur:cur + n], cur + n
+
+    def desc_for(self, kd, L):
+        t = self.torch
+        n_row = BATCH * kd * L
+        n_bc = BATCH * K_DIR * N_STATE * L
+        if self.cur_row + n_row > self.u.numel():
+            self.cur_row = 0
+        if self.cur_bc + n_bc > self.Bm.numel():
+            self.cur_bc = 0
+        r0, b0 = self.cur_row, self.cur_bc
+        self.cur_row += n_row
+        self.cur_bc += n_bc
+        d = self.Desc()
+        d.batch, d.dim, d.dstate, d.ngroups, d.seqlen = BATCH, kd, N_STATE, K_DIR, L
+        d.dtype, d.delta_softplus = 0, 1
+        p = lambda buf, off=0: ctypes.c_void_p(buf.data_ptr() + 4 * off)  # noqa: E731
+        d.u, d.delta, d.dout = p(self.u, r0), p(self.delta, r0), p(self.dout, r0)
+        d.B, d.C = p(self.Bm, b0), p(self.Cm, b0)
+        d.A, d.D, d.delta_bias = p(self.A), p(self.D), p(self.bias)
+        for s in (d.u_stride, d.delta_stride, d.out_stride, d.dout_stride):
+            s[0], s[1] = kd * L, L
+        for s in (d.B_stride, d.C_stride):
+            s[0], s[1], s[2] = K_DIR * N_STATE * L, N_STATE * L, L
+        d.A_stride = N_STATE
+        d.out, d.x = p(self.out), p(self.x)
+        d.du, d.ddelta = p(self.du), p(self.dd)
+        d.dA, d.dB, d.dC, d.dD, d.ddelta_bias = p(self.dA), p(self.dB), p(self.dC), p(self.dD), p(self.dbias)
+        _ = t
+        return d, n_bc
+
+    def step(self, stream, bwd_events=None):
+        """All 80 scans forward then backward (kernel launches + the dB/dC zero fills they need)."""
+        torch = self.torch
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        for kd, L in self.scans:
+            d, n_bc = self.desc_for(kd, L)
+            self.native.check(self.lib.nz_scan_fwd(ctypes.byref(d), sp), "nz_scan_fwd")
+            if (kd // K_DIR) != 8:  # several CTAs share a dB/dC element -> accumulate into zeros
+                self.dB[:n_bc].zero_()
+                self.dC[:n_bc].zero_()
+            if bwd_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            self.native.check(self.lib.nz_scan_bwd(ctypes.byref(d), sp), "nz_scan_bwd")
+            if bwd_events is not None:
+                e1.record(stream)
+                bwd_events.append((e0, e1))
+
+
+def e2e_run(dev, stream, steps, warmup):
+    """The same workload through the host-buffer C-ABI entry point (pinned host operands)."""
+    import torch
+
+    from nnuzoo_b200 import _native
+    from nnuzoo_b200._native import NzScanDesc
+
+    lib = _native.lib()
+    scans = m2net_scan_list(512)
+    row_max = max(BATCH * kd * L for kd, L in scans)
+    bc_max = max(BATCH * K_DIR * N_STATE * L for _, L in scans)
+    pin = lambda n: torch.empty(n, dtype=torch.float32, pin_memory=True)  # noqa: E731
+    g = torch.Generator(device=dev).manual_seed(99)
+    src_row = torch.randn(row_max, device=dev, generator=g)
+    src_bc = torch.randn(bc_max, device=dev, generator=g)
+    hu, hd, hgo = pin(row_max), pin(row_max), pin(row_max)
+    hB, hC = pin(bc_max), pin(bc_max)
+    hu.copy_(src_row)
+    hd.copy_(src_row * 0.5)
+    hgo.copy_(src_row.flip(0))
+    hB.copy_(src_bc)
+    hC.copy_(src_bc.flip(0))
+    del src_row, src_bc
+    ho, hdu, hdd = pin(row_max), pin(row_max), pin(row_max)
+    hdB, hdC = pin(bc_max), pin(bc_max)
+    kdm = max(kd for kd, _ in scans)
+    hA = (-torch.arange(1, N_STATE + 1).float().repeat(kdm, 1)).contiguous().pin_memory()
+    hD, hb = torch.ones(kdm).pin_memory(), torch.full((kdm,), -2.0).pin_memory()
+    hdA, hdD, hdb = torch.zeros(kdm, N_STATE).pin_memory(), torch.zeros(kdm).pin_memory(), torch.zeros(kdm).pin_memory()
+    torch.cuda.synchronize(dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    h2d = d2h = 0
+    for kd, L in scans:
+        b = scan_bytes(BATCH, kd, L)
+        h2d += 4 * (3 * b["E"] + 2 * b["S"]) + 4 * kd * (N_STATE + 2)
+        d2h += 4 * (3 * b["E"] + 2 * b["S"]) + 4 * kd * (N_STATE + 2)
+
+    def one_step():
+        for kd, L in scans:
+            d = NzScanDesc()
+            d.batch, d.dim, d.dstate, d.ngroups, d.seqlen = BATCH, kd, N_STATE, K_DIR, L
+            d.dtype, d.delta_softplus = 0, 1
+            d.u, d.delta, d.dout, d.B, d.C = p(hu), p(hd), p(hgo), p(hB), p(hC)
+            d.A, d.D, d.delta_bias = p(hA), p(hD), p(hb)
+            for s in (d.u_stride, d.delta_stride, d.out_stride, d.dout_stride):
+                s[0], s[1] = kd * L, L
+            for s in (d.B_stride, d.C_stride):
+                s[0], s[1], s[2] = K_DIR * N_STATE * L, N_STATE * L, L
+            d.A_stride = N_STATE
+            d.out, d.du, d.ddelta, d.dB, d.dC = p(ho), p(hdu), p(hdd), p(hdB), p(hdC)
+            d.dA, d.dD, d.ddelta_bias = p(hdA), p(hdD), p(hdb)
+            _native.check(lib.nz_scan_fwd_bwd_host(ctypes.byref(d), sp), "nz_scan_fwd_bwd_host")
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_step()
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / steps
+    assert bool(torch.isfinite(ho[:1024]).all())
+    return dt, h2d, d2h
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: this path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from nnuzoo_b200 import _native
+
+    wl = Workload(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, args.warmup)):
+        wl.step(stream)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _native.launch_count()
+    bwd_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        wl.step(stream, bwd_events)
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _native.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * wl.total_bytes / (ms_per_step * 1e-3) / 1e9
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_events)
+    bwd_gbps = wl.bwd_bytes * args.steps / (bwd_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+
+    e2e = None
+    cpu = None
+    if not args.no_e2e:
+        try:
+            dt, h2d, d2h = e2e_run(dev, stream, args.e2e_steps, 1)
+            barrier()
+            if world > 1:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            e2e = {"value": world * wl.total_bytes / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": dt * 1e3,
+                   "api": "nz_scan_fwd_bwd_host (include/nnuzoo_b200.h), pinned host buffers"}
+        except Exception as ex:  # report, never fake
+            e2e = {"value": None, "unit": "GB/s", "error": repr(ex)[:300]}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_sample_run(1, 1)
+        cpu = {"value": r["gbps"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+               "seconds": r["seconds"]}
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "patches_per_s_scan_only": world * BATCH / (ms_per_step * 1e-3),
+            "frac_of_hbm_peak": value / world / peak,
+            "roofline": {"bound": "hbm", "achieved": bwd_gbps, "peak": peak, "unit": "GB/s", "frac": bwd_gbps / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "nz::scan_bwd_kernel<float,8,32,8,TMA> (all 80 launches per step; "
+                                   "algorithmic bytes 4*(5E+4S) per launch)",
+                         "share_of_step": bwd_ms / (ms_per_step * args.steps)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

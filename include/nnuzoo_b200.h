@@ -1,0 +1,160 @@
+/*
+ * nnuzoo_b200.h -- C ABI of the B200-native selective-scan / SS2D hot path.
+ *
+ * This is the drop-in boundary.  The reference reaches its native code
+ * through a pybind module that is NOT in its tree (`selective_scan_cuda`, from mamba_ssm):
+ *
+ *   selective_scan_cuda.fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus) -> [out, x, (out_z)]
+ *       called at nnunetv2/nets/seg_mamba/selective_scan_interface.py:37
+ *   selective_scan_cuda.bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, out, dz,
+ *                           delta_softplus, recompute_out_z) -> [du, ddelta, dA, dB, dC, dD, ddelta_bias, (dz)]
+ *       called at nnunetv2/nets/seg_mamba/selective_scan_interface.py:62
+ *
+ * nz_scan_fwd / nz_scan_bwd replace exactly those two entry points; nz_cross_scan /
+ * nz_cross_merge replace the CrossScan / CrossMerge tensor shuffles that the reference writes
+ * inline in PyTorch (m2net.py:175-177, :202-206 + :218; ssnd2net.py:249-255, :285-299).
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - the caller owns and allocates every buffer (outputs, checkpoints, gradient accumulators);
+ *     kernels never allocate and never synchronise the device
+ *   - all launches go to the `stream` argument (a cudaStream_t passed as void*); the calls are
+ *     re-entrant, hold no global state and are CUDA-graph capturable
+ *   - strides are in ELEMENTS; the innermost (sequence) stride of u/delta/B/C/z/dout is 1, the same
+ *     constraint the reference enforces at selective_scan_interface.py:19-30
+ *   - return value: 0 on success, a negative NZ_E* code otherwise; nz_last_error() returns a
+ *     thread-local human-readable message.  No exceptions cross this boundary.
+ */
+#ifndef NNUZOO_B200_H
+#define NNUZOO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NZ_ABI_VERSION 1
+
+/* element types of u / delta / B / C / z / out / dout / du / ddelta / dz */
+#define NZ_F32 0
+#define NZ_BF16 1
+#define NZ_F16 2
+
+/* error codes */
+#define NZ_OK 0
+#define NZ_EINVAL (-1)      /* bad shape / stride / dtype / null pointer */
+#define NZ_EUNSUPPORTED (-2) /* valid request outside what the kernels implement (e.g. d_state > 16) */
+#define NZ_ECUDA (-3)       /* a CUDA runtime / driver call failed */
+
+/* The scan walks L in chunks of NZ_CHUNK steps; the forward saves the state at the end of every
+ * chunk ("x" of the reference ABI) and the backward recomputes inside a chunk from it. */
+#define NZ_CHUNK 256
+#define NZ_MAX_DSTATE 16
+
+typedef struct NzScanDesc {
+  /* ---- problem ---- */
+  int32_t batch;          /* B                                                     */
+  int32_t dim;            /* K*D rows per batch entry                              */
+  int32_t dstate;         /* N (<= NZ_MAX_DSTATE)                                  */
+  int32_t ngroups;        /* G: B/C are (batch, G, N, L); dim % G == 0             */
+  int64_t seqlen;         /* L                                                     */
+  int32_t dtype;          /* NZ_F32 / NZ_BF16 / NZ_F16                             */
+  int32_t delta_softplus; /* 0 / 1                                                 */
+  int32_t force_generic;  /* 1: never use the TMA path (testing)                   */
+  int32_t reserved0;
+
+  /* ---- forward inputs (selective_scan_cuda.fwd arguments) ---- */
+  const void* u;            /* (batch, dim, L)                 */
+  const void* delta;        /* (batch, dim, L)                 */
+  const float* A;           /* (dim, N) fp32, real             */
+  const void* B;            /* (batch, G, N, L)                */
+  const void* C;            /* (batch, G, N, L)                */
+  const float* D;           /* (dim) fp32 or NULL              */
+  const void* z;            /* (batch, dim, L) or NULL         */
+  const float* delta_bias;  /* (dim) fp32 or NULL              */
+  int64_t u_stride[2];      /* batch, dim                      */
+  int64_t delta_stride[2];
+  int64_t z_stride[2];
+  int64_t B_stride[3];      /* batch, group, state             */
+  int64_t C_stride[3];
+  int64_t A_stride;         /* row stride of A (state stride 1) */
+
+  /* ---- forward outputs ---- */
+  void* out;                /* (batch, dim, L): y + D*u, times SiLU(z) when z != NULL  */
+  int64_t out_stride[2];
+  float* x;                 /* (batch, dim, nz_scan_num_chunks(L), N) fp32 contiguous:
+                               state at the end of each chunk; x[..., -1, :] is last_state */
+
+  /* ---- backward inputs (in addition to the forward inputs and x) ---- */
+  const void* dout;         /* (batch, dim, L)                 */
+  int64_t dout_stride[2];
+
+  /* ---- backward outputs ---- */
+  void* du;                 /* (batch, dim, L), contiguous, dtype                         */
+  void* ddelta;             /* (batch, dim, L), contiguous, dtype                         */
+  void* dz;                 /* (batch, dim, L), contiguous, dtype; NULL iff z == NULL     */
+  float* dA;                /* (dim, N) fp32, contiguous      -- ACCUMULATED INTO: caller zeroes */
+  float* dB;                /* (batch, G, N, L) fp32 contiguous -- ACCUMULATED INTO: caller zeroes */
+  float* dC;                /* (batch, G, N, L) fp32 contiguous -- ACCUMULATED INTO: caller zeroes */
+  float* dD;                /* (dim) fp32 or NULL             -- ACCUMULATED INTO: caller zeroes */
+  float* ddelta_bias;       /* (dim) fp32 or NULL             -- ACCUMULATED INTO: caller zeroes */
+} NzScanDesc;
+
+/* Number of NZ_CHUNK-long chunks (second-to-last extent of the checkpoint tensor x). */
+int64_t nz_scan_num_chunks(int64_t seqlen);
+
+/* replaces selective_scan_cuda.fwd (selective_scan_interface.py:37) */
+int nz_scan_fwd(const NzScanDesc* desc, void* stream);
+
+/* replaces selective_scan_cuda.bwd (selective_scan_interface.py:62) */
+int nz_scan_bwd(const NzScanDesc* desc, void* stream);
+
+/*
+ * CrossScan: x (batch, dim, *spatial) -> xs (batch, K, dim, L), K = 2 * nspatial orders:
+ *   nspatial == 2 (H, W):    k0 row-major, k1 column-major, k2/k3 their L-flips  (m2net.py:175-177)
+ *   nspatial == 3 (Z, H, W): k0 "z h w", k1 "w z h", k2 "h w z", k3..5 flips     (ssnd2net.py:250-255)
+ * Pure data movement, bit-exact.  x and xs are contiguous; dtype is the element type of both.
+ */
+int nz_cross_scan(const void* x, void* xs, int32_t dtype, int32_t batch, int32_t dim, int32_t nspatial,
+                  const int64_t* spatial, void* stream);
+
+/*
+ * CrossMerge: out_y (batch, K, dim, L) fp32 -> y (batch, dim, L) fp32 in row-major spatial order,
+ * summed in the reference's association order (m2net.py:202-206 + :218; ssnd2net.py:286-298).
+ * mode 0 = reference (3-D: reproduces the reference's reuse of direction 1 / 4 and its ignoring of
+ * directions 2 / 5 bit-exactly), mode 1 = "fixed" 3-D merge (never used for parity).
+ */
+int nz_cross_merge(const float* out_y, float* y, int32_t batch, int32_t dim, int32_t nspatial,
+                   const int64_t* spatial, int32_t mode, void* stream);
+
+/* Adjoint of nz_cross_merge: dy (batch, dim, L) -> d_out_y (batch, K, dim, L).  (The adjoint of
+ * nz_cross_scan is nz_cross_merge with mode 1, so it needs no entry point of its own.) */
+int nz_cross_merge_bwd(const float* dy, float* d_out_y, int32_t batch, int32_t dim, int32_t nspatial,
+                       const int64_t* spatial, int32_t mode, void* stream);
+
+/*
+ * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):
+ * every pointer in `desc` is a HOST pointer, strides as above; the call stages host -> device,
+ * runs nz_scan_fwd (and nz_scan_bwd when desc->dout != NULL) and copies the results back,
+ * synchronising `stream` before returning.  Used by bench.py for the end-to-end number.
+ */
+int nz_scan_fwd_bwd_host(const NzScanDesc* desc_host, void* stream);
+
+/* Bind the calling thread to `device` inside this library's CUDA runtime instance (the library
+ * links cudart statically; one process per GPU calls this once with its LOCAL_RANK device). */
+int nz_set_device(int device);
+
+/* sizeof(NzScanDesc) as compiled into the library (lets FFI bindings verify their struct mirror) */
+int64_t nz_sizeof_scan_desc(void);
+
+const char* nz_last_error(void);
+int nz_abi_version(void);
+/* number of kernel launches this library has issued in the calling process (bench.py gpu_launches) */
+int64_t nz_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNUZOO_B200_H */

@@ -1,0 +1,337 @@
+// capi.cu -- the extern "C" boundary declared in include/nnuzoo_b200.h.
+//
+// Validation mirrors the constraints of the reference wrapper
+// (nnunetv2/nets/seg_mamba/selective_scan_interface.py:19-36: unit innermost stride, grouped B/C),
+// builds the TMA tensor maps from the caller's pointers + strides (no .contiguous() copies: the
+// SS2D callers pass B/C as split views, SURVEY.md hard part 5) and launches on the caller's stream.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/nnuzoo_b200.h"
+#include "scan_kernels.cuh"
+
+namespace nz {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static size_t esize(int dtype) { return dtype == NZ_F32 ? 4 : 2; }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Tensor map over a (…, rows, L) tensor viewed as (128-byte line, lines per row, outer dims…):
+// the smem image of a box is then dense rows of NZ_CHUNK elements, 128B-swizzled.
+static bool make_map(CUtensorMap* m, int dtype, const void* base, int nouter, const int64_t* outer_dim,
+                     const int64_t* outer_stride_elems, int64_t L, const int* outer_box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  const size_t es = esize(dtype);
+  const cuuint32_t inner = (cuuint32_t)(128 / es);
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  dims[0] = inner;
+  dims[1] = (cuuint64_t)(L * es / 128);
+  strides[0] = 128;
+  box[0] = inner;
+  box[1] = (cuuint32_t)(NZ_CHUNK * es / 128);
+  const cuuint64_t safe = (cuuint64_t)L * es;  // stride used for extent-1 dims (any 16B multiple works)
+  for (int i = 0; i < nouter; ++i) {
+    dims[2 + i] = (cuuint64_t)outer_dim[i];
+    cuuint64_t sb = (cuuint64_t)outer_stride_elems[i] * es;
+    if (outer_dim[i] == 1 && (sb == 0 || sb % 16 != 0)) sb = safe;
+    strides[1 + i] = sb;
+    box[2 + i] = (cuuint32_t)outer_box[i];
+  }
+  const CUtensorMapDataType dt = dtype == NZ_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == NZ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                    : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r = enc(m, dt, (cuuint32_t)(2 + nouter), const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// TMA can express a (batch, rows, L) operand iff every stride is a 16-byte multiple, the base is
+// 16-byte aligned and a row is a whole number of 128-byte lines.
+static bool tma_ok_rows(const void* p, int dtype, int64_t L, const int64_t* dims, const int64_t* strides, int n) {
+  const size_t es = esize(dtype);
+  if (!p || !aligned16(p) || (L * es) % 128 != 0) return false;
+  for (int i = 0; i < n; ++i)
+    if (dims[i] > 1 && ((strides[i] * (int64_t)es) % 16 != 0 || strides[i] <= 0)) return false;
+  return true;
+}
+
+static int validate(const NzScanDesc* d, bool bwd) {
+  if (!d) return fail(NZ_EINVAL, "null descriptor");
+  if (d->batch < 1 || d->dim < 1 || d->dstate < 1 || d->ngroups < 1 || d->seqlen < 1)
+    return fail(NZ_EINVAL, "batch/dim/dstate/ngroups/seqlen must be >= 1 (got %d %d %d %d %lld)", d->batch, d->dim,
+                d->dstate, d->ngroups, (long long)d->seqlen);
+  if (d->dstate > NZ_MAX_DSTATE)
+    return fail(NZ_EUNSUPPORTED, "d_state %d > %d is not implemented (nnUZoo uses 16)", d->dstate, NZ_MAX_DSTATE);
+  if (d->dim % d->ngroups) return fail(NZ_EINVAL, "dim %d is not a multiple of ngroups %d", d->dim, d->ngroups);
+  if (d->dtype != NZ_F32 && d->dtype != NZ_BF16 && d->dtype != NZ_F16) return fail(NZ_EINVAL, "bad dtype %d", d->dtype);
+  if (!d->u || !d->delta || !d->A || !d->B || !d->C) return fail(NZ_EINVAL, "u/delta/A/B/C must be non-null");
+  if (!d->x) return fail(NZ_EINVAL, "checkpoint buffer x must be non-null");
+  if (!bwd && !d->out) return fail(NZ_EINVAL, "out must be non-null");
+  if (bwd) {
+    if (!d->dout || !d->du || !d->ddelta || !d->dA || !d->dB || !d->dC)
+      return fail(NZ_EINVAL, "dout/du/ddelta/dA/dB/dC must be non-null for the backward");
+    if ((d->z != nullptr) != (d->dz != nullptr)) return fail(NZ_EINVAL, "dz must be given iff z is given");
+  }
+  if ((long long)d->batch * d->ngroups * d->dim > 2000000000LL) return fail(NZ_EINVAL, "grid too large");
+  return NZ_OK;
+}
+
+static void fill_args(const NzScanDesc* d, ScanKArgs& a) {
+  memset(&a, 0, sizeof(a));
+  a.u = d->u; a.delta = d->delta; a.z = d->z; a.dout = d->dout; a.B = d->B; a.C = d->C;
+  a.A = d->A; a.D = d->D; a.bias = d->delta_bias;
+  a.out = d->out; a.du = d->du; a.ddelta = d->ddelta; a.dz = d->dz;
+  a.x = d->x; a.dA = d->dA; a.dB = d->dB; a.dC = d->dC; a.dD = d->dD; a.dbias = d->ddelta_bias;
+  a.L = d->seqlen;
+  a.u_bs = d->u_stride[0]; a.u_ds = d->u_stride[1];
+  a.dl_bs = d->delta_stride[0]; a.dl_ds = d->delta_stride[1];
+  a.z_bs = d->z_stride[0]; a.z_ds = d->z_stride[1];
+  a.o_bs = d->out_stride[0]; a.o_ds = d->out_stride[1];
+  a.do_bs = d->dout_stride[0]; a.do_ds = d->dout_stride[1];
+  a.B_bs = d->B_stride[0]; a.B_gs = d->B_stride[1]; a.B_ns = d->B_stride[2];
+  a.C_bs = d->C_stride[0]; a.C_gs = d->C_stride[1]; a.C_ns = d->C_stride[2];
+  a.A_ds = d->A_stride;
+  a.batch = d->batch; a.dim = d->dim; a.dstate = d->dstate; a.ngroups = d->ngroups;
+  a.dpg = d->dim / d->ngroups;
+  a.nchunks = (int)nz_scan_num_chunks(d->seqlen);
+  a.softplus = d->delta_softplus;
+  const size_t es = esize(d->dtype);
+  a.vec_out = d->out && aligned16(d->out) && (d->out_stride[0] * es) % 16 == 0 && (d->out_stride[1] * es) % 16 == 0;
+  a.vec_grad = (d->seqlen * es) % 16 == 0 && (d->seqlen % 4 == 0) && (!d->du || aligned16(d->du)) &&
+               (!d->ddelta || aligned16(d->ddelta)) && (!d->dz || aligned16(d->dz)) && (!d->dB || aligned16(d->dB)) &&
+               (!d->dC || aligned16(d->dC));
+}
+
+// Decide the path and build the tensor maps.  Returns true when the TMA path is usable.
+static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
+  if (d->force_generic || d->dstate != NZ_MAX_DSTATE || a.dpg % 8 != 0) return false;
+  const int64_t rd[2] = {d->dim, d->batch};
+  const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
+  const int64_t ds[2] = {d->delta_stride[1], d->delta_stride[0]};
+  const int64_t zs[2] = {d->z_stride[1], d->z_stride[0]};
+  const int64_t os[2] = {d->dout_stride[1], d->dout_stride[0]};
+  const int64_t bd[3] = {d->dstate, d->ngroups, d->batch};
+  const int64_t bs[3] = {d->B_stride[2], d->B_stride[1], d->B_stride[0]};
+  const int64_t cs[3] = {d->C_stride[2], d->C_stride[1], d->C_stride[0]};
+  const int64_t L = d->seqlen;
+  if (!tma_ok_rows(d->u, d->dtype, L, rd, us, 2) || !tma_ok_rows(d->delta, d->dtype, L, rd, ds, 2) ||
+      !tma_ok_rows(d->B, d->dtype, L, bd, bs, 3) || !tma_ok_rows(d->C, d->dtype, L, bd, cs, 3))
+    return false;
+  if (d->z && !tma_ok_rows(d->z, d->dtype, L, rd, zs, 2)) return false;
+  if (bwd && !tma_ok_rows(d->dout, d->dtype, L, rd, os, 2)) return false;
+  if (bwd && !aligned16(d->x)) return false;
+  const int rbox[2] = {8, 1};
+  const int bbox[3] = {NZ_MAX_DSTATE, 1, 1};
+  bool ok = make_map(&a.tm_u, d->dtype, d->u, 2, rd, us, L, rbox) &&
+            make_map(&a.tm_delta, d->dtype, d->delta, 2, rd, ds, L, rbox) &&
+            make_map(&a.tm_B, d->dtype, d->B, 3, bd, bs, L, bbox) && make_map(&a.tm_C, d->dtype, d->C, 3, bd, cs, L, bbox);
+  if (ok && d->z) ok = make_map(&a.tm_z, d->dtype, d->z, 2, rd, zs, L, rbox);
+  if (ok && bwd) ok = make_map(&a.tm_dout, d->dtype, d->dout, 2, rd, os, L, rbox);
+  return ok;
+}
+
+static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
+  int rc = validate(d, bwd);
+  if (rc) return rc;
+  ScanKArgs a;
+  fill_args(d, a);
+  const bool tma = setup_tma(d, a, bwd);
+  const int rows = (a.dpg % 8 == 0) ? 8 : 1;
+  const bool has_z = d->z != nullptr;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (d->dtype == NZ_F32)
+    e = bwd ? launch_scan_bwd<float>(a, tma, has_z, rows, st) : launch_scan_fwd<float>(a, tma, has_z, rows, st);
+  else if (d->dtype == NZ_BF16)
+    e = bwd ? launch_scan_bwd<__nv_bfloat16>(a, tma, has_z, rows, st)
+            : launch_scan_fwd<__nv_bfloat16>(a, tma, has_z, rows, st);
+  else
+    e = bwd ? launch_scan_bwd<__half>(a, tma, has_z, rows, st) : launch_scan_fwd<__half>(a, tma, has_z, rows, st);
+  if (e != cudaSuccess)
+    return fail(NZ_ECUDA, "%s launch failed: %s (tma=%d rows=%d)", bwd ? "scan_bwd" : "scan_fwd", cudaGetErrorString(e),
+                (int)tma, rows);
+  count_launch(1);
+  return NZ_OK;
+}
+
+}  // namespace nz
+
+extern "C" {
+
+int64_t nz_scan_num_chunks(int64_t seqlen) { return (seqlen + NZ_CHUNK - 1) / NZ_CHUNK; }
+
+int nz_scan_fwd(const NzScanDesc* desc, void* stream) { return nz::run_scan(desc, stream, false); }
+
+int nz_scan_bwd(const NzScanDesc* desc, void* stream) { return nz::run_scan(desc, stream, true); }
+
+const char* nz_last_error(void) { return nz::g_err; }
+
+int nz_abi_version(void) { return NZ_ABI_VERSION; }
+
+int64_t nz_sizeof_scan_desc(void) { return (int64_t)sizeof(NzScanDesc); }
+
+int nz_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  return e == cudaSuccess ? NZ_OK : nz::fail(NZ_ECUDA, "cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+}
+
+int64_t nz_launch_count(void) { return (int64_t)nz::g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer entry point: stage H2D, run forward (+ backward), copy results D2H.
+// ------------------------------------------------------------------------------------------------
+#define NZ_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      rc = nz::fail(NZ_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e_));          \
+      goto done;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
+  if (!h) return nz::fail(NZ_EINVAL, "null descriptor");
+  NzScanDesc probe = *h;
+  if (!probe.x) probe.x = reinterpret_cast<float*>(16);  // x is optional on the host side
+  int rc = nz::validate(&probe, h->dout != nullptr);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t es = nz::esize(h->dtype);
+  const int64_t Bt = h->batch, Dm = h->dim, N = h->dstate, G = h->ngroups, L = h->seqlen;
+  const int64_t nch = nz_scan_num_chunks(L);
+  const size_t row_bytes = (size_t)Bt * Dm * L * es, bc_bytes = (size_t)Bt * G * N * L * es;
+  const size_t bc_f32 = (size_t)Bt * G * N * L * 4;
+  const bool bwd = h->dout != nullptr;
+  // the host tensors must be dense for the staged copies
+  if (h->u_stride[1] != L || h->u_stride[0] != Dm * L || h->delta_stride[1] != L || h->delta_stride[0] != Dm * L ||
+      h->B_stride[2] != L || h->B_stride[1] != N * L || h->B_stride[0] != G * N * L || h->C_stride[2] != L ||
+      h->C_stride[1] != N * L || h->C_stride[0] != G * N * L || h->out_stride[1] != L || h->out_stride[0] != Dm * L)
+    return nz::fail(NZ_EINVAL, "host entry point needs dense (contiguous) host tensors");
+  {
+    // keep the stream-ordered pool's memory across calls (default threshold 0 would hand it back
+    // to the driver at every synchronisation and re-allocate GBs per call)
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (pool_dev != dev) {
+      cudaMemPool_t mp;
+      if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+      pool_dev = dev;
+    }
+  }
+  NzScanDesc d = *h;
+  char* pool = nullptr;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    char* p = pool + off;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  const size_t total = 8 * (row_bytes + 256) + 2 * (bc_bytes + 256) + 2 * (bc_f32 + 256) +
+                       (size_t)Bt * Dm * nch * N * 4 + 6 * ((size_t)Dm * N * 4 + 256) + 4096;
+  NZ_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pool), total, st));
+  {
+    char* du_ = carve(row_bytes); char* dd_ = carve(row_bytes); char* dz_ = carve(row_bytes);
+    char* u_ = carve(row_bytes); char* dl_ = carve(row_bytes); char* z_ = carve(row_bytes);
+    char* out_ = carve(row_bytes); char* go_ = carve(row_bytes);
+    char* B_ = carve(bc_bytes); char* C_ = carve(bc_bytes);
+    char* dB_ = carve(bc_f32); char* dC_ = carve(bc_f32);
+    char* x_ = carve((size_t)Bt * Dm * nch * N * 4);
+    char* A_ = carve((size_t)Dm * N * 4); char* dA_ = carve((size_t)Dm * N * 4);
+    char* D_ = carve((size_t)Dm * 4); char* bias_ = carve((size_t)Dm * 4);
+    char* dD_ = carve((size_t)Dm * 4); char* db_ = carve((size_t)Dm * 4);
+    NZ_CUDA(cudaMemcpyAsync(u_, h->u, row_bytes, cudaMemcpyHostToDevice, st));
+    NZ_CUDA(cudaMemcpyAsync(dl_, h->delta, row_bytes, cudaMemcpyHostToDevice, st));
+    NZ_CUDA(cudaMemcpyAsync(B_, h->B, bc_bytes, cudaMemcpyHostToDevice, st));
+    NZ_CUDA(cudaMemcpyAsync(C_, h->C, bc_bytes, cudaMemcpyHostToDevice, st));
+    NZ_CUDA(cudaMemcpyAsync(A_, h->A, (size_t)Dm * N * 4, cudaMemcpyHostToDevice, st));
+    d.u = u_; d.delta = dl_; d.B = B_; d.C = C_; d.A = reinterpret_cast<float*>(A_); d.A_stride = N;
+    d.out = out_; d.x = reinterpret_cast<float*>(x_);
+    if (h->D) { NZ_CUDA(cudaMemcpyAsync(D_, h->D, (size_t)Dm * 4, cudaMemcpyHostToDevice, st)); d.D = reinterpret_cast<float*>(D_); }
+    if (h->delta_bias) {
+      NZ_CUDA(cudaMemcpyAsync(bias_, h->delta_bias, (size_t)Dm * 4, cudaMemcpyHostToDevice, st));
+      d.delta_bias = reinterpret_cast<float*>(bias_);
+    }
+    if (h->z) {
+      NZ_CUDA(cudaMemcpyAsync(z_, h->z, row_bytes, cudaMemcpyHostToDevice, st));
+      d.z = z_; d.z_stride[0] = Dm * L; d.z_stride[1] = L;
+    }
+    rc = nz_scan_fwd(&d, stream);
+    if (rc) goto done;
+    NZ_CUDA(cudaMemcpyAsync(h->out, out_, row_bytes, cudaMemcpyDeviceToHost, st));
+    if (h->x) NZ_CUDA(cudaMemcpyAsync(h->x, x_, (size_t)Bt * Dm * nch * N * 4, cudaMemcpyDeviceToHost, st));
+    if (bwd) {
+      NZ_CUDA(cudaMemcpyAsync(go_, h->dout, row_bytes, cudaMemcpyHostToDevice, st));
+      d.dout = go_; d.dout_stride[0] = Dm * L; d.dout_stride[1] = L;
+      d.du = du_; d.ddelta = dd_; d.dz = h->z ? dz_ : nullptr;
+      d.dA = reinterpret_cast<float*>(dA_); d.dB = reinterpret_cast<float*>(dB_); d.dC = reinterpret_cast<float*>(dC_);
+      d.dD = h->dD ? reinterpret_cast<float*>(dD_) : nullptr;
+      d.ddelta_bias = h->ddelta_bias ? reinterpret_cast<float*>(db_) : nullptr;
+      NZ_CUDA(cudaMemsetAsync(dA_, 0, (size_t)Dm * N * 4, st));
+      NZ_CUDA(cudaMemsetAsync(dB_, 0, bc_f32, st));
+      NZ_CUDA(cudaMemsetAsync(dC_, 0, bc_f32, st));
+      NZ_CUDA(cudaMemsetAsync(dD_, 0, (size_t)Dm * 4, st));
+      NZ_CUDA(cudaMemsetAsync(db_, 0, (size_t)Dm * 4, st));
+      rc = nz_scan_bwd(&d, stream);
+      if (rc) goto done;
+      NZ_CUDA(cudaMemcpyAsync(h->du, du_, row_bytes, cudaMemcpyDeviceToHost, st));
+      NZ_CUDA(cudaMemcpyAsync(h->ddelta, dd_, row_bytes, cudaMemcpyDeviceToHost, st));
+      if (h->z) NZ_CUDA(cudaMemcpyAsync(h->dz, dz_, row_bytes, cudaMemcpyDeviceToHost, st));
+      NZ_CUDA(cudaMemcpyAsync(h->dA, dA_, (size_t)Dm * N * 4, cudaMemcpyDeviceToHost, st));
+      NZ_CUDA(cudaMemcpyAsync(h->dB, dB_, bc_f32, cudaMemcpyDeviceToHost, st));
+      NZ_CUDA(cudaMemcpyAsync(h->dC, dC_, bc_f32, cudaMemcpyDeviceToHost, st));
+      if (h->dD) NZ_CUDA(cudaMemcpyAsync(h->dD, dD_, (size_t)Dm * 4, cudaMemcpyDeviceToHost, st));
+      if (h->ddelta_bias) NZ_CUDA(cudaMemcpyAsync(h->ddelta_bias, db_, (size_t)Dm * 4, cudaMemcpyDeviceToHost, st));
+    }
+  }
+done:
+  if (pool) cudaFreeAsync(pool, st);
+  {
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (!rc && e2 != cudaSuccess) rc = nz::fail(NZ_ECUDA, "stream sync failed: %s", cudaGetErrorString(e2));
+  }
+  return rc;
+}
+
+}  // extern "C"

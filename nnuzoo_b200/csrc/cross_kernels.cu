@@ -1,0 +1,211 @@
+// cross_kernels.cu -- CrossScan / CrossMerge sequence permutations of SS2D (2-D, 4 directions) and
+// SSND (3-D, 6 directions) as stand-alone, bit-exact data-movement kernels.
+//
+// Reference statements (pure PyTorch tensor shuffles, materialised copies):
+//   scan  2-D: nnunetv2/nets/m2net.py:175-177       3-D: nnunetv2/nets/ssnd2net.py:250-255
+//   merge 2-D: nnunetv2/nets/m2net.py:202-206, :218 3-D: nnunetv2/nets/ssnd2net.py:286-298
+//
+// Index maps (l = position in the scanned sequence, src = row-major spatial offset):
+//   2-D  k0: src = l                      k1: src = (l % H) * W + l / H           k2,k3: same at L-1-l
+//   3-D  k0: src = l                      k1 "w z h": l = (w*Z + z)*H + h         k2 "h w z": l = (h*W + w)*Z + z
+//        k3..5: same at L-1-l
+// The merge sums in the reference's left-to-right order with separate fp32 adds, so results are
+// bit-identical to the PyTorch expressions.  One thread per output element, writes coalesced.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nnuzoo_b200.h"
+
+namespace nz {
+void count_launch(int n);
+
+struct Dims {
+  long Z, H, W, L;
+  int nsp;
+};
+
+// spatial offset visited at step l of forward direction kf (0..nsp-1)
+__device__ __forceinline__ long src_of(const Dims& s, int kf, long l) {
+  if (kf == 0) return l;
+  if (s.nsp == 2) {  // column-major walk
+    const long h = l % s.H, w = l / s.H;
+    return h * s.W + w;
+  }
+  if (kf == 1) {  // "w z h"
+    const long h = l % s.H, z = (l / s.H) % s.Z, w = l / (s.H * s.Z);
+    return (z * s.H + h) * s.W + w;
+  }
+  // kf == 2, "h w z"
+  const long z = l % s.Z, w = (l / s.Z) % s.W, h = l / (s.Z * s.W);
+  return (z * s.H + h) * s.W + w;
+}
+
+// step of forward direction kf that visits spatial offset src (inverse of src_of)
+__device__ __forceinline__ long step_of(const Dims& s, int kf, long src) {
+  if (kf == 0) return src;
+  if (s.nsp == 2) {
+    const long w = src % s.W, h = src / s.W;
+    return w * s.H + h;
+  }
+  const long w = src % s.W, h = (src / s.W) % s.H, z = src / (s.W * s.H);
+  if (kf == 1) return (w * s.Z + z) * s.H + h;
+  return (h * s.W + w) * s.Z + z;
+}
+
+template <typename T>
+__global__ void cross_scan_kernel(const T* __restrict__ x, T* __restrict__ xs, long rows /*batch*dim*/, int dim,
+                                  Dims s) {
+  const int K = 2 * s.nsp;
+  const long total = rows * K * s.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long l = i % s.L;
+    const long q = i / s.L;  // (b, k, d) flattened
+    const int dd = (int)(q % dim);
+    const int k = (int)((q / dim) % K);
+    const long b = q / ((long)dim * K);
+    const int kf = k % s.nsp;
+    const long ll = k >= s.nsp ? s.L - 1 - l : l;
+    xs[i] = x[(b * dim + dd) * s.L + src_of(s, kf, ll)];
+  }
+}
+
+// out_y (b, K, d, L) -> y (b, d, L)
+__global__ void cross_merge_kernel(const float* __restrict__ oy, float* __restrict__ y, long rows, int dim, Dims s,
+                                   int mode) {
+  const int K = 2 * s.nsp;
+  const long total = rows * s.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long l = i % s.L;
+    const long q = i / s.L;
+    const int dd = (int)(q % dim);
+    const long b = q / dim;
+    const float* base = oy + (b * K * dim + dd) * s.L;  // direction k at base + k*dim*L
+    const long ks = (long)dim * s.L;
+    float acc = base[l];                                      // out_y[:, 0]
+    acc = acc + base[s.nsp * ks + (s.L - 1 - l)];             // + inv_y[:, 0]
+    if (s.nsp == 2) {
+      const long j = step_of(s, 1, l);
+      acc = acc + base[ks + j];                               // + wh_y
+      acc = acc + base[3 * ks + (s.L - 1 - j)];               // + invwh_y
+    } else {
+      const long j1 = step_of(s, 1, l);
+      acc = acc + base[ks + j1];                              // + y_wzh        (ssnd2net.py:291)
+      acc = acc + base[4 * ks + (s.L - 1 - j1)];              // + inv_y_wzh    (:292)
+      if (mode == 0) {
+        // :295-296 -- direction 1 again, through a (W, Z, H)-shaped view whose axes are relabelled
+        // "h w z": output flat index l decomposes over sizes (H, W, Z) as (i2, i0, i1).
+        const long i1 = l % s.Z, i0 = (l / s.Z) % s.W, i2 = l / (s.Z * s.W);
+        const long j2 = (i0 * s.Z + i1) * s.H + i2;
+        acc = acc + base[ks + j2];
+        acc = acc + base[4 * ks + (s.L - 1 - j2)];
+      } else {
+        const long j2 = step_of(s, 2, l);
+        acc = acc + base[2 * ks + j2];
+        acc = acc + base[5 * ks + (s.L - 1 - j2)];
+      }
+    }
+    y[i] = acc;
+  }
+}
+
+// adjoint of cross_merge: dy (b, d, L) -> d_out_y (b, K, d, L)
+__global__ void cross_merge_bwd_kernel(const float* __restrict__ dy, float* __restrict__ doy, long rows, int dim,
+                                       Dims s, int mode) {
+  const int K = 2 * s.nsp;
+  const long total = rows * K * s.L;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long l = i % s.L;
+    const long q = i / s.L;
+    const int dd = (int)(q % dim);
+    const int k = (int)((q / dim) % K);
+    const long b = q / ((long)dim * K);
+    const float* g = dy + (b * dim + dd) * s.L;
+    const int kf = k % s.nsp;
+    const long ll = k >= s.nsp ? s.L - 1 - l : l;  // step index in the un-flipped direction
+    float v;
+    if (s.nsp == 2 || mode != 0) {
+      v = g[src_of(s, kf, ll)];
+    } else if (kf == 0) {
+      v = g[ll];
+    } else if (kf == 1) {
+      // contributions through :291/:292 and through the relabelled view of :295/:296
+      const long i2 = ll % s.H, i1 = (ll / s.H) % s.Z, i0 = ll / (s.H * s.Z);
+      v = g[src_of(s, 1, ll)] + g[(i2 * s.W + i0) * s.Z + i1];
+    } else {
+      v = 0.f;  // directions 2 and 5 never reach the reference's output
+    }
+    doy[i] = v;
+  }
+}
+
+static int launch_cfg(long total, int* grid) {
+  const int threads = 256;
+  long blocks = (total + threads - 1) / threads;
+  const long cap = 148L * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  *grid = (int)blocks;
+  return threads;
+}
+
+static bool make_dims(int nsp, const int64_t* sp, Dims* d) {
+  if (!sp || (nsp != 2 && nsp != 3)) return false;
+  d->nsp = nsp;
+  d->Z = nsp == 3 ? sp[0] : 1;
+  d->H = sp[nsp - 2];
+  d->W = sp[nsp - 1];
+  if (d->Z < 1 || d->H < 1 || d->W < 1) return false;
+  d->L = d->Z * d->H * d->W;
+  return true;
+}
+
+}  // namespace nz
+
+extern "C" {
+
+int nz_cross_scan(const void* x, void* xs, int32_t dtype, int32_t batch, int32_t dim, int32_t nspatial,
+                  const int64_t* spatial, void* stream) {
+  nz::Dims s;
+  if (!x || !xs || batch < 1 || dim < 1 || !nz::make_dims(nspatial, spatial, &s)) return NZ_EINVAL;
+  const long rows = (long)batch * dim;
+  int grid;
+  const int threads = nz::launch_cfg(rows * 2 * nspatial * s.L, &grid);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == NZ_F32)
+    nz::cross_scan_kernel<uint32_t><<<grid, threads, 0, st>>>(static_cast<const uint32_t*>(x),
+                                                              static_cast<uint32_t*>(xs), rows, dim, s);
+  else if (dtype == NZ_BF16 || dtype == NZ_F16)
+    nz::cross_scan_kernel<uint16_t><<<grid, threads, 0, st>>>(static_cast<const uint16_t*>(x),
+                                                              static_cast<uint16_t*>(xs), rows, dim, s);
+  else
+    return NZ_EINVAL;
+  nz::count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+}
+
+int nz_cross_merge(const float* out_y, float* y, int32_t batch, int32_t dim, int32_t nspatial,
+                   const int64_t* spatial, int32_t mode, void* stream) {
+  nz::Dims s;
+  if (!out_y || !y || batch < 1 || dim < 1 || !nz::make_dims(nspatial, spatial, &s)) return NZ_EINVAL;
+  const long rows = (long)batch * dim;
+  int grid;
+  const int threads = nz::launch_cfg(rows * s.L, &grid);
+  nz::cross_merge_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out_y, y, rows, dim, s, mode);
+  nz::count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+}
+
+int nz_cross_merge_bwd(const float* dy, float* d_out_y, int32_t batch, int32_t dim, int32_t nspatial,
+                       const int64_t* spatial, int32_t mode, void* stream) {
+  nz::Dims s;
+  if (!dy || !d_out_y || batch < 1 || dim < 1 || !nz::make_dims(nspatial, spatial, &s)) return NZ_EINVAL;
+  const long rows = (long)batch * dim;
+  int grid;
+  const int threads = nz::launch_cfg(rows * 2 * nspatial * s.L, &grid);
+  nz::cross_merge_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, d_out_y, rows, dim, s,
+                                                                                          mode);
+  nz::count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+}
+
+}  // extern "C"

@@ -1,0 +1,186 @@
+"""Drop-in for the reference's operator layer, backed by the sm_100a kernels.
+
+Mirrors nnunetv2/nets/seg_mamba/selective_scan_interface.py:14-83 (``SelectiveScanFn`` /
+``selective_scan_fn``; the models import the same-named function from
+``mamba_ssm.ops.selective_scan_interface``): same signature, same argument meaning, same returns
+(``out`` in the dtype and shape of ``u``; ``(out, last_state)`` when ``return_last_state``; the
+gradient of ``last_state`` is ignored, :79-82), same tuple order of gradients (:69-74).
+
+Where the reference calls ``selective_scan_cuda.fwd`` / ``.bwd`` (:37, :62) this calls
+``nz_scan_fwd`` / ``nz_scan_bwd`` of include/nnuzoo_b200.h.  There is no CPU path: CPU tensors
+raise, and a missing native library raises at first use.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import NzScanDesc
+
+_DTYPES = {torch.float32: _native.NZ_F32, torch.bfloat16: _native.NZ_BF16, torch.float16: _native.NZ_F16}
+
+# rows of one (batch, group) handled per CTA by the fast kernels (scan_inst.cuh); when a group has
+# exactly this many rows a single CTA owns each dB/dC element and no zero-initialisation is needed
+_ROWS_PER_CTA = 8
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_inputs(u, delta, A, B, C, D, z, delta_bias):
+    if not u.is_cuda:
+        raise RuntimeError("nnuzoo_b200.selective_scan_fn: tensors must live on a CUDA device "
+                           "(there is no CPU fallback; the CPU oracle lives under oracle/ for tests only)")
+    if u.dtype not in _DTYPES:
+        raise TypeError(f"unsupported dtype {u.dtype}")
+    if A.is_complex():
+        raise NotImplementedError("complex A is not used by nnUZoo and is not implemented")
+    if B.dim() < 3 or C.dim() < 3:
+        raise NotImplementedError("only input-dependent (variable) B and C are implemented "
+                                  "(the only form nnUZoo uses)")
+    if u.dim() != 3 or delta.shape != u.shape:
+        raise ValueError("u and delta must both be (batch, dim, L)")
+    if A.dim() != 2 or A.shape[0] != u.shape[1]:
+        raise ValueError("A must be (dim, dstate)")
+    if A.shape[1] > _native.NZ_MAX_DSTATE:
+        raise NotImplementedError(f"d_state {A.shape[1]} > {_native.NZ_MAX_DSTATE} is not implemented")
+
+
+def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, force_generic):
+    batch, dim, L = u.shape
+    desc.batch, desc.dim, desc.dstate, desc.ngroups = batch, dim, A.shape[1], B.shape[1]
+    desc.seqlen = L
+    desc.dtype = _DTYPES[u.dtype]
+    desc.delta_softplus = int(bool(delta_softplus))
+    desc.force_generic = int(bool(force_generic))
+    desc.u, desc.delta, desc.A, desc.B, desc.C = _ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C)
+    desc.D, desc.z, desc.delta_bias = _ptr(D), _ptr(z), _ptr(delta_bias)
+    desc.u_stride[0], desc.u_stride[1] = u.stride(0), u.stride(1)
+    desc.delta_stride[0], desc.delta_stride[1] = delta.stride(0), delta.stride(1)
+    if z is not None:
+        desc.z_stride[0], desc.z_stride[1] = z.stride(0), z.stride(1)
+    for k in range(3):
+        desc.B_stride[k] = B.stride(k)
+        desc.C_stride[k] = C.stride(k)
+    desc.A_stride = A.stride(0)
+
+
+_FORCE_GENERIC = False  # tests flip this to exercise the non-TMA loader on TMA-eligible shapes
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    """Same contract as the reference's ``SelectiveScanFn`` (selective_scan_interface.py:14-74)."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                return_last_state=False):
+        _check_inputs(u, delta, A, B, C, D, z, delta_bias)
+        ctx.in_dtypes = tuple(None if t is None else t.dtype for t in (delta, A, B, C, D, z, delta_bias))
+        # :19-30 -- only the innermost stride has to be 1; outer strides are passed to the kernel
+        if u.stride(-1) != 1:
+            u = u.contiguous()
+        if delta.stride(-1) != 1 or delta.dtype != u.dtype:
+            delta = delta.to(u.dtype).contiguous()
+        if D is not None:
+            D = D.float().contiguous()
+        if delta_bias is not None:
+            delta_bias = delta_bias.float().contiguous()
+        if B.stride(-1) != 1 or B.dtype != u.dtype:
+            B = B.to(u.dtype).contiguous()
+        if C.stride(-1) != 1 or C.dtype != u.dtype:
+            C = C.to(u.dtype).contiguous()
+        if z is not None and (z.stride(-1) != 1 or z.dtype != u.dtype):
+            z = z.to(u.dtype).contiguous()
+        A = A.float()
+        if A.stride(-1) != 1:
+            A = A.contiguous()
+        # :31-36 -- 3-D B/C get a singleton group axis
+        ctx.squeeze_B = B.dim() == 3
+        ctx.squeeze_C = C.dim() == 3
+        if ctx.squeeze_B:
+            B = B.unsqueeze(1)
+        if ctx.squeeze_C:
+            C = C.unsqueeze(1)
+        batch, dim, L = u.shape
+        N = A.shape[1]
+        if B.shape != (batch, B.shape[1], N, L) or C.shape != B.shape:
+            raise ValueError(f"B/C must be (batch, groups, dstate, L); got {tuple(B.shape)} {tuple(C.shape)}")
+        if dim % B.shape[1]:
+            raise ValueError("dim must be a multiple of the number of B/C groups")
+
+        lib = _native.lib()
+        _native.bind_device(u.device.index)
+        nchunks = (L + _native.NZ_CHUNK - 1) // _native.NZ_CHUNK
+        out = torch.empty((batch, dim, L), dtype=u.dtype, device=u.device)
+        x = torch.empty((batch, dim, nchunks, N), dtype=torch.float32, device=u.device)
+        desc = NzScanDesc()
+        _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC)
+        desc.out = _ptr(out)
+        desc.out_stride[0], desc.out_stride[1] = out.stride(0), out.stride(1)
+        desc.x = _ptr(x)
+        with torch.cuda.device(u.device):
+            _native.check(lib.nz_scan_fwd(ctypes.byref(desc), _stream(u.device)), "nz_scan_fwd")
+        ctx.delta_softplus = bool(delta_softplus)
+        ctx.has_z = z is not None
+        ctx.has_D = D is not None
+        ctx.has_bias = delta_bias is not None
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x)
+        if not return_last_state:
+            return out
+        last_state = x[:, :, -1, :]  # :40 (batch, dim, dstate)
+        ctx.mark_non_differentiable(last_state)
+        return out, last_state
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, z, delta_bias, x = ctx.saved_tensors
+        if dout.stride(-1) != 1 or dout.dtype != u.dtype:  # :57-58
+            dout = dout.to(u.dtype).contiguous()
+        batch, dim, L = u.shape
+        N, G = A.shape[1], B.shape[1]
+        dev = u.device
+        lib = _native.lib()
+        _native.bind_device(dev.index)
+        du = torch.empty((batch, dim, L), dtype=u.dtype, device=dev)
+        ddelta = torch.empty_like(du)
+        dz = torch.empty_like(du) if ctx.has_z else None
+        dA = torch.zeros((dim, N), dtype=torch.float32, device=dev)
+        dpg = dim // G
+        single_owner = dpg == (_ROWS_PER_CTA if dpg % _ROWS_PER_CTA == 0 else 1)
+        mk = torch.empty if single_owner else torch.zeros
+        dB = mk((batch, G, N, L), dtype=torch.float32, device=dev)
+        dC = mk((batch, G, N, L), dtype=torch.float32, device=dev)
+        dD = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_D else None
+        dbias = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_bias else None
+        desc = NzScanDesc()
+        _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC)
+        desc.x = _ptr(x)
+        desc.dout = _ptr(dout)
+        desc.dout_stride[0], desc.dout_stride[1] = dout.stride(0), dout.stride(1)
+        desc.du, desc.ddelta, desc.dz = _ptr(du), _ptr(ddelta), _ptr(dz)
+        desc.dA, desc.dB, desc.dC, desc.dD, desc.ddelta_bias = _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias)
+        with torch.cuda.device(dev):
+            _native.check(lib.nz_scan_bwd(ctypes.byref(desc), _stream(dev)), "nz_scan_bwd")
+        if ctx.squeeze_B:  # :67-68
+            dB = dB.squeeze(1)
+        if ctx.squeeze_C:
+            dC = dC.squeeze(1)
+        # gradients leave in the dtype their inputs arrived in
+        t_delta, t_A, t_B, t_C, t_D, t_z, t_bias = ctx.in_dtypes
+        cast = lambda g, t: g if g is None or g.dtype == t else g.to(t)  # noqa: E731
+        return (du, cast(ddelta, t_delta), cast(dA, t_A), cast(dB, t_B), cast(dC, t_C), cast(dD, t_D),
+                cast(dz, t_z), cast(dbias, t_bias), None, None)  # order of :69-74
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                      return_last_state=False):
+    """if return_last_state is True, returns (out, last_state); last_state has shape
+    (batch, dim, dstate) and carries no gradient (selective_scan_interface.py:77-83)."""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
