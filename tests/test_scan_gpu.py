@@ -62,8 +62,8 @@ def test_golden_forward_backward(name):
     gout = torch.from_numpy(rec["in_gout"]).to(_dev()).to(getattr(torch, dt))
     out, last, grads = _run(inp, softplus, gout)
     assert out.dtype == getattr(torch, dt) and tuple(out.shape) == rec["out"].shape
-    assert rel_err(out.float().cpu().numpy(), rec["out"]) < TOL[dt]
-    assert rel_err(last.cpu().numpy(), rec["last_state"]) < TOL[dt]
+    assert rel_err(out.detach().float().cpu().numpy(), rec["out"]) < TOL[dt]
+    assert rel_err(last.detach().cpu().numpy(), rec["last_state"]) < TOL[dt]
     for g, k in GRADS.items():
         if "grad_" + k in rec:
             got = grads[g].float().cpu().numpy()
@@ -134,7 +134,7 @@ def _compare(inp_cpu, gout_cpu, dt, force_generic=False, keep_views=False):
     torch.cuda.synchronize()
     ref_out, ref_last, ref_g = _oracle(inp_cpu, gout_cpu)
     tol = TOL[dt]
-    errs = {"out": rel_err(out.float().cpu().numpy(), ref_out), "last": rel_err(last.cpu().numpy(), ref_last)}
+    errs = {"out": rel_err(out.detach().float().cpu().numpy(), ref_out), "last": rel_err(last.detach().cpu().numpy(), ref_last)}
     if keep_views:
         R = parent.shape[2] - 2 * N
         pg = parent.grad.float().cpu().numpy()

@@ -40,7 +40,7 @@ def run_stage(stage):
         f = {k: (None if v is None else v.float()) for k, v in inp.items()}
         ro, rl = scan_oracle.selective_scan_oracle(f["u"], f["delta"], f["A"], f["B"], f["C"], f["D"], f["z"],
                                                    f["delta_bias"], True, True, precision="f64")
-        res = {"out": rel(out.float().cpu().numpy(), ro), "last": rel(last.cpu().numpy(), rl)}
+        res = {"out": rel(out.detach().float().cpu().numpy(), ro), "last": rel(last.detach().cpu().numpy(), rl)}
         if bwd:
             out.backward(gout.to(dev))
             torch.cuda.synchronize()
