@@ -352,7 +352,8 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(3, args.warmup)):
+    min_warm = 0 if os.environ.get("NZ_BENCH_PROFILE") else 3  # profiling runs may skip the warm-up
+    for _ in range(max(min_warm, args.warmup)):
         wl.step(stream)
     barrier()
     sampler = ClockSampler(local)

@@ -10,7 +10,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnnuzoo_b200.so")
+# NNUZOO_B200_LIB lets the tuning tools load an alternative build of the same ABI
+LIB_PATH = os.environ.get("NNUZOO_B200_LIB") or os.path.join(_HERE, "lib", "libnnuzoo_b200.so")
 
 NZ_F32, NZ_BF16, NZ_F16 = 0, 1, 2
 NZ_CHUNK = 256

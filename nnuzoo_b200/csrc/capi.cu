@@ -13,7 +13,7 @@
 #include <cstring>
 
 #include "../../include/nnuzoo_b200.h"
-#include "scan_kernels.cuh"
+#include "scan_inst.cuh"
 
 namespace nz {
 
@@ -141,7 +141,7 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a) {
 }
 
 // Decide the path and build the tensor maps.  Returns true when the TMA path is usable.
-static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
+static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd, int rows_per_cta) {
   if (d->force_generic || d->dstate != NZ_MAX_DSTATE || a.dpg % 8 != 0) return false;
   const int64_t rd[2] = {d->dim, d->batch};
   const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
@@ -158,7 +158,7 @@ static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   if (d->z && !tma_ok_rows(d->z, d->dtype, L, rd, zs, 2)) return false;
   if (bwd && !tma_ok_rows(d->dout, d->dtype, L, rd, os, 2)) return false;
   if (bwd && !aligned16(d->x)) return false;
-  const int rbox[2] = {8, 1};
+  const int rbox[2] = {rows_per_cta, 1};
   const int bbox[3] = {NZ_MAX_DSTATE, 1, 1};
   bool ok = make_map(&a.tm_u, d->dtype, d->u, 2, rd, us, L, rbox) &&
             make_map(&a.tm_delta, d->dtype, d->delta, 2, rd, ds, L, rbox) &&
@@ -173,8 +173,16 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   if (rc) return rc;
   ScanKArgs a;
   fill_args(d, a);
-  const bool tma = setup_tma(d, a, bwd);
-  const int rows = (a.dpg % 8 == 0) ? 8 : 1;
+  int rows = (a.dpg % 8 == 0) ? 8 : 1;
+#if NZ_FWD_M16
+  // forward fast path: 16 rows per CTA (two per warp) when the group allows it and TMA applies
+  if (!bwd && a.dpg % 16 == 0 && !d->force_generic && d->dstate == NZ_MAX_DSTATE) rows = 16;
+#endif
+  bool tma = setup_tma(d, a, bwd, rows);
+  if (!tma && rows == 16) {
+    rows = 8;
+    tma = setup_tma(d, a, bwd, rows);
+  }
   const bool has_z = d->z != nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e;

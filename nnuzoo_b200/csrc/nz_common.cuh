@@ -41,6 +41,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// plain arrive (release.cta): used for the CTA-internal producer/consumer hand-offs
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -55,6 +59,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+
+// "Last warp out issues the refill": every warp calls this once it no longer needs a shared-memory
+// buffer; it returns true (warp-uniformly) in the warp that arrived last, which then re-arms the
+// counter and may overwrite the buffer (e.g. issue the next TMA load into it).  No thread waits.
+__device__ __forceinline__ bool warp_last_arrival(unsigned* cnt, unsigned nwarps, int lane) {
+  __syncwarp();
+  unsigned old = 0;
+  if (lane == 0) {
+    __threadfence_block();  // this warp's reads of the buffer are performed before the arrival
+    old = atomicAdd(cnt, 1u);
+    if (old == nwarps - 1) {
+      atomicExch(cnt, 0u);
+      __threadfence_block();
+    }
+  }
+  old = __shfl_sync(0xffffffffu, old, 0);
+  return old == nwarps - 1;
 }
 
 // ------------------------------------- TMA ------------------------------------------------------
@@ -94,10 +116,88 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// F.softplus with threshold 20 (selective_scan_interface.py:107); evaluated once per (row, t),
-// amortised over the 16 states, so the accurate libm forms are affordable.
-__device__ __forceinline__ float softplus_f(float x) { return x > 20.f ? x : log1pf(__expf(x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// F.softplus with threshold 20 (selective_scan_interface.py:107), branch-free:
+//   t = e^x;  log1p(t) = t - t^2/2 + t^3/3 for t < 0.01 (|err| < t^4/4), else ln2 * lg2(1 + t).
+// Relative error ~2e-5 at worst (lg2.approx near 1), far inside the 1e-3 budget.
+__device__ __forceinline__ float softplus_f(float x) {
+  const float t = ex2_approx(fminf(x, 20.f) * kLog2e);
+  const float series = t * fmaf(t, fmaf(t, 0.33333334f, -0.5f), 1.f);
+  const float viaLog = kLn2 * lg2_approx(1.f + t);
+  const float sp = t < 0.01f ? series : viaLog;
+  return x > 20.f ? x : sp;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return __fdividef(1.f, 1.f + ex2_approx(-x * kLog2e)); }
+// sigmoid(x) expressed through dl = softplus(x):  1 - e^{-dl}  (series below 0.02 to avoid cancellation)
+__device__ __forceinline__ float sigmoid_from_softplus(float dl) {
+  const float e = ex2_approx(-dl * kLog2e);
+  const float series = dl * fmaf(dl, fmaf(dl, 0.16666667f, -0.5f), 1.f);
+  return dl < 0.02f ? series : 1.f - e;
+}
+
+// ---- Kogge-Stone steps on (P, H) pairs of the affine recurrence h <- P*h + H ----------------------
+// The shuffle's own predicate output ("source lane in range") guards the combine, so no lane-index
+// compares or selects are needed.  kClampUp/Down encode the sub-warp width LPR for shfl.sync.
+template <int LPR>
+struct ShflClamp {
+  static constexpr unsigned kUp = (unsigned)(32 - LPR) << 8;
+  static constexpr unsigned kDown = ((unsigned)(32 - LPR) << 8) | 0x1fu;
+};
+// inclusive scan towards higher lanes: (P,H)[s] <- (P,H)[s] o (P,H)[s-off]
+template <int LPR>
+__device__ __forceinline__ void ks_up(float& P, float& H, int off) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 pp, hp;\n\t"
+      "shfl.sync.up.b32 pp|p, %0, %2, %3, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 hp, %1, %2, %3, 0xffffffff;\n\t"
+      "@p fma.rn.f32 %1, %0, hp, %1;\n\t"
+      "@p mul.f32 %0, %0, pp;\n\t}"
+      : "+f"(P), "+f"(H)
+      : "r"(off), "n"(ShflClamp<LPR>::kUp));
+}
+// inclusive scan towards lower lanes (suffix): (Q,G)[s] <- (Q,G)[s] o (Q,G)[s+off]
+template <int LPR>
+__device__ __forceinline__ void ks_down(float& Q, float& G, int off) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 qq, gg;\n\t"
+      "shfl.sync.down.b32 qq|p, %0, %2, %3, 0xffffffff;\n\t"
+      "shfl.sync.down.b32 gg, %1, %2, %3, 0xffffffff;\n\t"
+      "@p fma.rn.f32 %1, %0, gg, %1;\n\t"
+      "@p mul.f32 %0, %0, qq;\n\t}"
+      : "+f"(Q), "+f"(G)
+      : "r"(off), "n"(ShflClamp<LPR>::kDown));
+}
+// value entering this lane's segment: carry (first lane) or P[s-1]*carry + H[s-1]
+template <int LPR>
+__device__ __forceinline__ float ks_enter_up(float P, float H, float carry) {
+  float h;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 pp, hp;\n\t"
+      "shfl.sync.up.b32 pp|p, %1, 1, %4, 0xffffffff;\n\t"
+      "shfl.sync.up.b32 hp, %2, 1, %4, 0xffffffff;\n\t"
+      "mov.f32 %0, %3;\n\t"
+      "@p fma.rn.f32 %0, pp, %3, hp;\n\t}"
+      : "=f"(h)
+      : "f"(P), "f"(H), "f"(carry), "n"(ShflClamp<LPR>::kUp));
+  return h;
+}
+template <int LPR>
+__device__ __forceinline__ float ks_enter_down(float Q, float G, float carry) {
+  float h;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 qq, gg;\n\t"
+      "shfl.sync.down.b32 qq|p, %1, 1, %4, 0xffffffff;\n\t"
+      "shfl.sync.down.b32 gg, %2, 1, %4, 0xffffffff;\n\t"
+      "mov.f32 %0, %3;\n\t"
+      "@p fma.rn.f32 %0, qq, %3, gg;\n\t}"
+      : "=f"(h)
+      : "f"(Q), "f"(G), "f"(carry), "n"(ShflClamp<LPR>::kDown));
+  return h;
+}
 
 // ------------------------------------- element types --------------------------------------------
 template <typename T>
