@@ -166,6 +166,17 @@ CONFIG = {"workload": "configs[1]: all 80 SS2D selective scans (fwd+bwd) of one 
           "parallelism": "replicas (one full batch per GPU, no data-path collective)"}
 
 
+def max_over_ranks(value: float, dev, world: int) -> float:
+    """Multi-GPU numbers are the max over ranks (NCCL on the GPU box, gloo in the CPU tests)."""
+    if world <= 1:
+        return value
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 # -------------------------------------------------------------------------------------------------
 # GPU arm
 # -------------------------------------------------------------------------------------------------
@@ -369,11 +380,7 @@ def run_gpu_arm(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     launches = _native.launch_count() - n0
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1), dev, world)
     ms_per_step = ms / args.steps
     value = world * wl.total_bytes / (ms_per_step * 1e-3) / 1e9
     bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_events)
@@ -386,10 +393,7 @@ def run_gpu_arm(args):
         try:
             dt, h2d, d2h = e2e_run(dev, stream, args.e2e_steps, 1)
             barrier()
-            if world > 1:
-                t = torch.tensor([dt], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dt = float(t.item())
+            dt = max_over_ranks(dt, dev, world)
             e2e = {"value": world * wl.total_bytes / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "ms_per_step": dt * 1e3,
                    "api": "nz_scan_fwd_bwd_host (include/nnuzoo_b200.h), pinned host buffers"}
