@@ -214,8 +214,10 @@ class Workload:
         self.dA = torch.zeros(kdm, N_STATE, device=dev)
         self.dD = torch.zeros(kdm, device=dev)
         self.dbias = torch.zeros(kdm, device=dev)
-        nch_max = max(BATCH * kd * ((L + 255) // 256) * N_STATE for kd, L in self.scans)
+        ck = self.native.NZ_CHUNK
+        nch_max = max(BATCH * kd * ((L + ck - 1) // ck) * N_STATE for kd, L in self.scans)
         self.x = torch.empty(nch_max, device=dev)
+        self.ws = torch.empty(self.native.workspace_bytes(BATCH, kdm), dtype=torch.uint8, device=dev)
         self.cur_row = 0
         self.cur_bc = 0
         self.total_bytes = sum(scan_bytes(BATCH, kd, L)["total"] for kd, L in self.scans)
@@ -250,6 +252,7 @@ class Workload:
             s[0], s[1], s[2] = K_DIR * N_STATE * L, N_STATE * L, L
         d.A_stride = N_STATE
         d.out, d.x = p(self.out), p(self.x)
+        d.workspace, d.workspace_bytes = p(self.ws), self.native.workspace_bytes(BATCH, kd)
         d.du, d.ddelta = p(self.du), p(self.dd)
         d.dA, d.dB, d.dC, d.dD, d.ddelta_bias = p(self.dA), p(self.dB), p(self.dC), p(self.dD), p(self.dbias)
         _ = t
@@ -262,7 +265,7 @@ class Workload:
         for kd, L in self.scans:
             d, n_bc = self.desc_for(kd, L)
             self.native.check(self.lib.nz_scan_fwd(ctypes.byref(d), sp), "nz_scan_fwd")
-            if (kd // K_DIR) != 8:  # several CTAs share a dB/dC element -> accumulate into zeros
+            if (kd // K_DIR) > 16:  # several tiles share a dB/dC element -> accumulate into zeros
                 self.dB[:n_bc].zero_()
                 self.dC[:n_bc].zero_()
             if bwd_events is not None:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NZ_ABI_VERSION 1
+#define NZ_ABI_VERSION 2
 
 /* element types of u / delta / B / C / z / out / dout / du / ddelta / dz */
 #define NZ_F32 0
@@ -48,9 +48,9 @@ extern "C" {
 #define NZ_EUNSUPPORTED (-2) /* valid request outside what the kernels implement (e.g. d_state > 16) */
 #define NZ_ECUDA (-3)       /* a CUDA runtime / driver call failed */
 
-/* The scan walks L in chunks of NZ_CHUNK steps; the forward saves the state at the end of every
- * chunk ("x" of the reference ABI) and the backward recomputes inside a chunk from it. */
-#define NZ_CHUNK 256
+/* The forward saves the state h every NZ_CHUNK steps ("x" of the reference ABI); the backward
+ * recomputes inside a chunk from it. */
+#define NZ_CHUNK 128
 #define NZ_MAX_DSTATE 16
 
 typedef struct NzScanDesc {
@@ -100,7 +100,17 @@ typedef struct NzScanDesc {
   float* dC;                /* (batch, G, N, L) fp32 contiguous -- ACCUMULATED INTO: caller zeroes */
   float* dD;                /* (dim) fp32 or NULL             -- ACCUMULATED INTO: caller zeroes */
   float* ddelta_bias;       /* (dim) fp32 or NULL             -- ACCUMULATED INTO: caller zeroes */
+
+  /* ---- scratch (both directions) ---- */
+  void* workspace;          /* >= nz_scan_workspace_bytes() bytes, 256-byte aligned; the call zeroes it on
+                               `stream` itself.  Holds the tile ticket counter and the {value, tag} slots
+                               through which consecutive chunks of a row hand their state over.  Two calls
+                               that may run concurrently need separate workspaces. */
+  int64_t workspace_bytes;
 } NzScanDesc;
+
+/* Bytes of scratch a call with this batch / dim needs (same for forward and backward). */
+int64_t nz_scan_workspace_bytes(const NzScanDesc* desc);
 
 /* Number of NZ_CHUNK-long chunks (second-to-last extent of the checkpoint tensor x). */
 int64_t nz_scan_num_chunks(int64_t seqlen);

@@ -14,8 +14,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NNUZOO_B200_LIB") or os.path.join(_HERE, "lib", "libnnuzoo_b200.so")
 
 NZ_F32, NZ_BF16, NZ_F16 = 0, 1, 2
-NZ_CHUNK = 256
+NZ_CHUNK = 128
 NZ_MAX_DSTATE = 16
+ABI_VERSION = 2
+WS_HEADER = 256
 
 _vp = ctypes.c_void_p
 _i32 = ctypes.c_int32
@@ -37,6 +39,7 @@ class NzScanDesc(ctypes.Structure):
         ("dout", _vp), ("dout_stride", _i64 * 2),
         ("du", _vp), ("ddelta", _vp), ("dz", _vp), ("dA", _vp), ("dB", _vp), ("dC", _vp), ("dD", _vp),
         ("ddelta_bias", _vp),
+        ("workspace", _vp), ("workspace_bytes", _i64),
     ]
 
 
@@ -62,6 +65,8 @@ def lib():
                 L = ctypes.CDLL(LIB_PATH)
                 L.nz_scan_num_chunks.argtypes = [_i64]
                 L.nz_scan_num_chunks.restype = _i64
+                L.nz_scan_workspace_bytes.argtypes = [ctypes.POINTER(NzScanDesc)]
+                L.nz_scan_workspace_bytes.restype = _i64
                 for name in ("nz_scan_fwd", "nz_scan_bwd", "nz_scan_fwd_bwd_host"):
                     fn = getattr(L, name)
                     fn.argtypes = [ctypes.POINTER(NzScanDesc), _vp]
@@ -80,7 +85,7 @@ def lib():
                 L.nz_sizeof_scan_desc.restype = _i64
                 if L.nz_sizeof_scan_desc() != ctypes.sizeof(NzScanDesc):
                     raise NativeLibraryError("NzScanDesc layout differs between _native.py and the .so")
-                if L.nz_abi_version() != 1:
+                if L.nz_abi_version() != ABI_VERSION:
                     raise NativeLibraryError("ABI version mismatch between _native.py and the .so")
                 _lib = L
     return _lib
@@ -98,6 +103,11 @@ def bind_device(index: int) -> None:
     if _bound_device.get(tid) != index:
         check(lib().nz_set_device(int(index)), "nz_set_device")
         _bound_device[tid] = index
+
+
+def workspace_bytes(batch: int, dim: int) -> int:
+    """Scratch bytes of one scan call (mirror of nz_scan_workspace_bytes; checked in tests/test_abi.py)."""
+    return WS_HEADER + batch * dim * 2 * NZ_MAX_DSTATE * 8
 
 
 def launch_count() -> int:

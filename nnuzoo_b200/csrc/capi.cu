@@ -32,6 +32,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static size_t esize(int dtype) { return dtype == NZ_F32 ? 4 : 2; }
 
+constexpr size_t kWsHeader = 256;  // ticket counter (+ padding) in front of the hand-off slots
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -51,7 +53,7 @@ static EncodeTiledFn get_encode() {
 // Tensor map over a (…, rows, L) tensor viewed as (128-byte line, lines per row, outer dims…):
 // the smem image of a box is then dense rows of NZ_CHUNK elements, 128B-swizzled.
 static bool make_map(CUtensorMap* m, int dtype, const void* base, int nouter, const int64_t* outer_dim,
-                     const int64_t* outer_stride_elems, int64_t L, const int* outer_box) {
+                     const int64_t* outer_stride_elems, int64_t L, const int* outer_box, int tile_len) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   const size_t es = esize(dtype);
@@ -63,7 +65,7 @@ static bool make_map(CUtensorMap* m, int dtype, const void* base, int nouter, co
   dims[1] = (cuuint64_t)(L * es / 128);
   strides[0] = 128;
   box[0] = inner;
-  box[1] = (cuuint32_t)(NZ_CHUNK * es / 128);
+  box[1] = (cuuint32_t)(tile_len * es / 128);
   const cuuint64_t safe = (cuuint64_t)L * es;  // stride used for extent-1 dims (any 16B multiple works)
   for (int i = 0; i < nouter; ++i) {
     dims[2 + i] = (cuuint64_t)outer_dim[i];
@@ -104,6 +106,10 @@ static int validate(const NzScanDesc* d, bool bwd) {
   if (d->dtype != NZ_F32 && d->dtype != NZ_BF16 && d->dtype != NZ_F16) return fail(NZ_EINVAL, "bad dtype %d", d->dtype);
   if (!d->u || !d->delta || !d->A || !d->B || !d->C) return fail(NZ_EINVAL, "u/delta/A/B/C must be non-null");
   if (!d->x) return fail(NZ_EINVAL, "checkpoint buffer x must be non-null");
+  if (!d->workspace || d->workspace_bytes < nz_scan_workspace_bytes(d))
+    return fail(NZ_EINVAL, "workspace must hold nz_scan_workspace_bytes() = %lld bytes (got %lld)",
+                (long long)nz_scan_workspace_bytes(d), (long long)d->workspace_bytes);
+  if (reinterpret_cast<uintptr_t>(d->workspace) & 255u) return fail(NZ_EINVAL, "workspace must be 256-byte aligned");
   if (!bwd && !d->out) return fail(NZ_EINVAL, "out must be non-null");
   if (bwd) {
     if (!d->dout || !d->du || !d->ddelta || !d->dA || !d->dB || !d->dC)
@@ -114,7 +120,7 @@ static int validate(const NzScanDesc* d, bool bwd) {
   return NZ_OK;
 }
 
-static void fill_args(const NzScanDesc* d, ScanKArgs& a) {
+static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   memset(&a, 0, sizeof(a));
   a.u = d->u; a.delta = d->delta; a.z = d->z; a.dout = d->dout; a.B = d->B; a.C = d->C;
   a.A = d->A; a.D = d->D; a.bias = d->delta_bias;
@@ -131,7 +137,14 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a) {
   a.A_ds = d->A_stride;
   a.batch = d->batch; a.dim = d->dim; a.dstate = d->dstate; a.ngroups = d->ngroups;
   a.dpg = d->dim / d->ngroups;
-  a.nchunks = (int)nz_scan_num_chunks(d->seqlen);
+  const int rows = bwd ? kBwdRows : kFwdRows, tl = bwd ? kBwdTL : kFwdTL;
+  a.nrb = (a.dpg + rows - 1) / rows;
+  a.nrb_total = d->batch * d->ngroups * a.nrb;
+  a.nchunks = (int)((d->seqlen + tl - 1) / tl);
+  a.nck = (int)nz_scan_num_chunks(d->seqlen);
+  a.ntiles = a.nrb_total * a.nchunks;
+  a.ticket = reinterpret_cast<unsigned*>(d->workspace);
+  a.carry = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d->workspace) + kWsHeader);
   a.softplus = d->delta_softplus;
   const size_t es = esize(d->dtype);
   a.vec_out = d->out && aligned16(d->out) && (d->out_stride[0] * es) % 16 == 0 && (d->out_stride[1] * es) % 16 == 0;
@@ -141,8 +154,9 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a) {
 }
 
 // Decide the path and build the tensor maps.  Returns true when the TMA path is usable.
-static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd, int rows_per_cta) {
-  if (d->force_generic || d->dstate != NZ_MAX_DSTATE || a.dpg % 8 != 0) return false;
+static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
+  const int rows_per_cta = bwd ? kBwdRows : kFwdRows, tl = bwd ? kBwdTL : kFwdTL;
+  if (d->force_generic || d->dstate != NZ_MAX_DSTATE || a.dpg % rows_per_cta != 0) return false;
   const int64_t rd[2] = {d->dim, d->batch};
   const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
   const int64_t ds[2] = {d->delta_stride[1], d->delta_stride[0]};
@@ -157,14 +171,13 @@ static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd, int rows_per_
     return false;
   if (d->z && !tma_ok_rows(d->z, d->dtype, L, rd, zs, 2)) return false;
   if (bwd && !tma_ok_rows(d->dout, d->dtype, L, rd, os, 2)) return false;
-  if (bwd && !aligned16(d->x)) return false;
   const int rbox[2] = {rows_per_cta, 1};
   const int bbox[3] = {NZ_MAX_DSTATE, 1, 1};
-  bool ok = make_map(&a.tm_u, d->dtype, d->u, 2, rd, us, L, rbox) &&
-            make_map(&a.tm_delta, d->dtype, d->delta, 2, rd, ds, L, rbox) &&
-            make_map(&a.tm_B, d->dtype, d->B, 3, bd, bs, L, bbox) && make_map(&a.tm_C, d->dtype, d->C, 3, bd, cs, L, bbox);
-  if (ok && d->z) ok = make_map(&a.tm_z, d->dtype, d->z, 2, rd, zs, L, rbox);
-  if (ok && bwd) ok = make_map(&a.tm_dout, d->dtype, d->dout, 2, rd, os, L, rbox);
+  bool ok = make_map(&a.tm_u, d->dtype, d->u, 2, rd, us, L, rbox, tl) &&
+            make_map(&a.tm_delta, d->dtype, d->delta, 2, rd, ds, L, rbox, tl) &&
+            make_map(&a.tm_B, d->dtype, d->B, 3, bd, bs, L, bbox, tl) && make_map(&a.tm_C, d->dtype, d->C, 3, bd, cs, L, bbox, tl);
+  if (ok && d->z) ok = make_map(&a.tm_z, d->dtype, d->z, 2, rd, zs, L, rbox, tl);
+  if (ok && bwd) ok = make_map(&a.tm_dout, d->dtype, d->dout, 2, rd, os, L, rbox, tl);
   return ok;
 }
 
@@ -172,31 +185,22 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   int rc = validate(d, bwd);
   if (rc) return rc;
   ScanKArgs a;
-  fill_args(d, a);
-  int rows = (a.dpg % 8 == 0) ? 8 : 1;
-#if NZ_FWD_M16
-  // forward fast path: 16 rows per CTA (two per warp) when the group allows it and TMA applies
-  if (!bwd && a.dpg % 16 == 0 && !d->force_generic && d->dstate == NZ_MAX_DSTATE) rows = 16;
-#endif
-  bool tma = setup_tma(d, a, bwd, rows);
-  if (!tma && rows == 16) {
-    rows = 8;
-    tma = setup_tma(d, a, bwd, rows);
-  }
+  fill_args(d, a, bwd);
+  if ((long long)a.nrb_total * a.nchunks > 2000000000LL) return fail(NZ_EINVAL, "too many tiles");
+  const bool tma = setup_tma(d, a, bwd);
   const bool has_z = d->z != nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  cudaError_t e;
+  cudaError_t e = cudaMemsetAsync(d->workspace, 0, (size_t)nz_scan_workspace_bytes(d), st);
+  if (e != cudaSuccess) return fail(NZ_ECUDA, "workspace memset failed: %s", cudaGetErrorString(e));
   if (d->dtype == NZ_F32)
-    e = bwd ? launch_scan_bwd<float>(a, tma, has_z, rows, st) : launch_scan_fwd<float>(a, tma, has_z, rows, st);
+    e = bwd ? launch_scan_bwd<float>(a, tma, has_z, st) : launch_scan_fwd<float>(a, tma, has_z, st);
   else if (d->dtype == NZ_BF16)
-    e = bwd ? launch_scan_bwd<__nv_bfloat16>(a, tma, has_z, rows, st)
-            : launch_scan_fwd<__nv_bfloat16>(a, tma, has_z, rows, st);
+    e = bwd ? launch_scan_bwd<__nv_bfloat16>(a, tma, has_z, st) : launch_scan_fwd<__nv_bfloat16>(a, tma, has_z, st);
   else
-    e = bwd ? launch_scan_bwd<__half>(a, tma, has_z, rows, st) : launch_scan_fwd<__half>(a, tma, has_z, rows, st);
+    e = bwd ? launch_scan_bwd<__half>(a, tma, has_z, st) : launch_scan_fwd<__half>(a, tma, has_z, st);
   if (e != cudaSuccess)
-    return fail(NZ_ECUDA, "%s launch failed: %s (tma=%d rows=%d)", bwd ? "scan_bwd" : "scan_fwd", cudaGetErrorString(e),
-                (int)tma, rows);
-  count_launch(1);
+    return fail(NZ_ECUDA, "%s launch failed: %s (tma=%d)", bwd ? "scan_bwd" : "scan_fwd", cudaGetErrorString(e), (int)tma);
+  count_launch(1);  // (the workspace memset is a driver memset node, not one of our kernels)
   return NZ_OK;
 }
 
@@ -205,6 +209,12 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
 extern "C" {
 
 int64_t nz_scan_num_chunks(int64_t seqlen) { return (seqlen + NZ_CHUNK - 1) / NZ_CHUNK; }
+
+int64_t nz_scan_workspace_bytes(const NzScanDesc* d) {
+  if (!d || d->batch < 1 || d->dim < 1) return 0;
+  // ticket header + per (batch, dim) row: 2 ring slots x 16 states x {fp32 value, u32 tag}
+  return (int64_t)nz::kWsHeader + (int64_t)d->batch * d->dim * 2 * NZ_MAX_DSTATE * 8;
+}
 
 int nz_scan_fwd(const NzScanDesc* desc, void* stream) { return nz::run_scan(desc, stream, false); }
 
@@ -239,6 +249,8 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
   if (!h) return nz::fail(NZ_EINVAL, "null descriptor");
   NzScanDesc probe = *h;
   if (!probe.x) probe.x = reinterpret_cast<float*>(16);  // x is optional on the host side
+  probe.workspace = reinterpret_cast<void*>(256);        // scratch is allocated here
+  probe.workspace_bytes = nz_scan_workspace_bytes(h);
   int rc = nz::validate(&probe, h->dout != nullptr);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -277,7 +289,8 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
     return p;
   };
   const size_t total = 8 * (row_bytes + 256) + 2 * (bc_bytes + 256) + 2 * (bc_f32 + 256) +
-                       (size_t)Bt * Dm * nch * N * 4 + 6 * ((size_t)Dm * N * 4 + 256) + 4096;
+                       (size_t)Bt * Dm * nch * N * 4 + 6 * ((size_t)Dm * N * 4 + 256) + 4096 +
+                       (size_t)nz_scan_workspace_bytes(h) + 256;
   NZ_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pool), total, st));
   {
     char* du_ = carve(row_bytes); char* dd_ = carve(row_bytes); char* dz_ = carve(row_bytes);
@@ -289,6 +302,8 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
     char* A_ = carve((size_t)Dm * N * 4); char* dA_ = carve((size_t)Dm * N * 4);
     char* D_ = carve((size_t)Dm * 4); char* bias_ = carve((size_t)Dm * 4);
     char* dD_ = carve((size_t)Dm * 4); char* db_ = carve((size_t)Dm * 4);
+    d.workspace = carve((size_t)nz_scan_workspace_bytes(h));
+    d.workspace_bytes = nz_scan_workspace_bytes(h);
     NZ_CUDA(cudaMemcpyAsync(u_, h->u, row_bytes, cudaMemcpyHostToDevice, st));
     NZ_CUDA(cudaMemcpyAsync(dl_, h->delta, row_bytes, cudaMemcpyHostToDevice, st));
     NZ_CUDA(cudaMemcpyAsync(B_, h->B, bc_bytes, cudaMemcpyHostToDevice, st));

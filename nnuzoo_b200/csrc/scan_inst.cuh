@@ -6,62 +6,83 @@
 
 namespace nz {
 
-constexpr int kM = 8;     // time steps per lane
-constexpr int kLPR = 32;  // lanes per row  (kM * kLPR == NZ_CHUNK)
-// forward fast path (TMA, 16 rows per CTA): 16 steps per lane, two rows per warp -> the two half-warps
-// read the same B/C words (broadcast), 4 scan rounds instead of 5
-#ifndef NZ_FWD_M16
-#define NZ_FWD_M16 0  // measured: 2.81 vs 2.86 clk/elt/SM when rows are plentiful, 5.4 vs 4.1 when they are not (96 CTAs)
+// Tile shapes (time steps per lane M, lane segments per row LPR; a warp owns 32/LPR rows):
+//   forward : 16 x 16 -> tiles of 16 rows x 256 steps (two checkpoints per tile)
+//   backward:  8 x 16 -> tiles of 16 rows x 128 steps (one checkpoint interval)
+#ifndef NZ_FWD_M
+#define NZ_FWD_M 16
 #endif
+#ifndef NZ_FWD_LPR
+#define NZ_FWD_LPR 16
+#endif
+#ifndef NZ_FWD_NQ
+#define NZ_FWD_NQ 1
+#endif
+#ifndef NZ_BWD_M
+#define NZ_BWD_M 8
+#endif
+#ifndef NZ_BWD_LPR
+#define NZ_BWD_LPR 16
+#endif
+constexpr int kWarps = 8;
+constexpr int kFwdRows = (32 / NZ_FWD_LPR) * kWarps, kFwdTL = NZ_FWD_M * NZ_FWD_LPR;
+constexpr int kBwdRows = (32 / NZ_BWD_LPR) * kWarps, kBwdTL = NZ_BWD_M * NZ_BWD_LPR;
 
-template <typename T, int WARPS, bool kTMA, bool kHasZ, int M = kM, int LPR = kLPR, int NQ = 2>
+// Persistent grid: as many CTAs as fit on the device (or as there are tiles).
+template <typename K>
+static cudaError_t persistent_grid(K kern, int threads, size_t smem, int ntiles, unsigned* grid) {
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return e;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  const long cap = (long)sms * per_sm;
+  *grid = (unsigned)(ntiles < cap ? ntiles : cap);
+  return cudaSuccess;
+}
+
+template <typename T, bool kTMA, bool kHasZ>
 static cudaError_t launch_fwd_one(const ScanKArgs& a, cudaStream_t st) {
-  using Cfg = ScanCfg<T, M, LPR, WARPS, kHasZ, false>;
-  auto kern = scan_fwd_kernel<T, M, LPR, WARPS, NQ, kTMA, kHasZ>;
+  using Cfg = ScanCfg<T, NZ_FWD_M, NZ_FWD_LPR, kWarps, kHasZ, false>;
+  auto kern = scan_fwd_kernel<T, NZ_FWD_M, NZ_FWD_LPR, kWarps, NZ_FWD_NQ, kTMA, kHasZ>;
   const size_t smem = Cfg::smem_bytes(kTMA);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const unsigned grid = (unsigned)a.batch * a.ngroups * (a.dpg / Cfg::R);
-  kern<<<grid, WARPS * 32, smem, st>>>(a);
+  unsigned grid = 0;
+  e = persistent_grid(kern, kWarps * 32, smem, a.ntiles, &grid);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kWarps * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 
-template <typename T, int WARPS, bool kTMA, bool kHasZ>
+template <typename T, bool kTMA, bool kHasZ>
 static cudaError_t launch_bwd_one(const ScanKArgs& a, cudaStream_t st) {
-  using Cfg = ScanCfg<T, kM, kLPR, WARPS, kHasZ, true>;
-  auto kern = scan_bwd_kernel<T, kM, kLPR, WARPS, kTMA, kHasZ>;
+  using Cfg = ScanCfg<T, NZ_BWD_M, NZ_BWD_LPR, kWarps, kHasZ, true>;
+  auto kern = scan_bwd_kernel<T, NZ_BWD_M, NZ_BWD_LPR, kWarps, kTMA, kHasZ>;
   const size_t smem = Cfg::smem_bytes(kTMA);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  const unsigned grid = (unsigned)a.batch * a.ngroups * (a.dpg / Cfg::R);
-  kern<<<grid, WARPS * 32, smem, st>>>(a);
+  unsigned grid = 0;
+  e = persistent_grid(kern, kWarps * 32, smem, a.ntiles, &grid);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kWarps * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 
-#define NZ_DISPATCH16(T)                                                                     \
-  if (rows_per_cta == 16 && tma)                                                             \
-    return has_z ? launch_fwd_one<T, 8, true, true, 16, 16, 1>(a, stream)                    \
-                 : launch_fwd_one<T, 8, true, false, 16, 16, 1>(a, stream);
-
-#define NZ_DISPATCH(FN, T)                                                                   \
-  if (rows_per_cta == 8) {                                                                   \
-    if (tma) return has_z ? FN<T, 8, true, true>(a, stream) : FN<T, 8, true, false>(a, stream);   \
-    return has_z ? FN<T, 8, false, true>(a, stream) : FN<T, 8, false, false>(a, stream);     \
-  }                                                                                          \
-  if (rows_per_cta == 1 && !tma)                                                             \
-    return has_z ? FN<T, 1, false, true>(a, stream) : FN<T, 1, false, false>(a, stream);     \
-  return cudaErrorInvalidConfiguration;
+#define NZ_DISPATCH(FN, T)                                                                  \
+  if (tma) return has_z ? FN<T, true, true>(a, stream) : FN<T, true, false>(a, stream);      \
+  return has_z ? FN<T, false, true>(a, stream) : FN<T, false, false>(a, stream);
 
 #define NZ_INSTANTIATE_SCAN(T)                                                               \
   template <>                                                                                \
-  cudaError_t launch_scan_fwd<T>(const ScanKArgs& a, bool tma, bool has_z, int rows_per_cta, \
-                                 cudaStream_t stream) {                                      \
-    NZ_DISPATCH16(T)                                                                         \
+  cudaError_t launch_scan_fwd<T>(const ScanKArgs& a, bool tma, bool has_z, cudaStream_t stream) { \
     NZ_DISPATCH(launch_fwd_one, T)                                                           \
   }                                                                                          \
   template <>                                                                                \
-  cudaError_t launch_scan_bwd<T>(const ScanKArgs& a, bool tma, bool has_z, int rows_per_cta, \
-                                 cudaStream_t stream) {                                      \
+  cudaError_t launch_scan_bwd<T>(const ScanKArgs& a, bool tma, bool has_z, cudaStream_t stream) { \
     NZ_DISPATCH(launch_bwd_one, T)                                                           \
   }
 

@@ -21,9 +21,9 @@ from ._native import NzScanDesc
 
 _DTYPES = {torch.float32: _native.NZ_F32, torch.bfloat16: _native.NZ_BF16, torch.float16: _native.NZ_F16}
 
-# rows of one (batch, group) handled per CTA by the fast kernels (scan_inst.cuh); when a group has
-# exactly this many rows a single CTA owns each dB/dC element and no zero-initialisation is needed
-_ROWS_PER_CTA = 8
+# rows of one (batch, group) in a backward tile (scan_inst.cuh kBwdRows); when a group has at most
+# this many rows a single tile owns each dB/dC element and no zero-initialisation is needed
+_ROWS_PER_TILE = 16
 
 
 def _ptr(t):
@@ -70,6 +70,12 @@ def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, forc
         desc.B_stride[k] = B.stride(k)
         desc.C_stride[k] = C.stride(k)
     desc.A_stride = A.stride(0)
+    # scratch for the tile tickets and the chained state hand-off; the call zeroes it on the stream.
+    # (the caching allocator orders its reuse after this stream's launches)
+    nbytes = _native.workspace_bytes(batch, dim)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=u.device)
+    desc.workspace, desc.workspace_bytes = _ptr(ws), nbytes
+    return ws
 
 
 _FORCE_GENERIC = False  # tests flip this to exercise the non-TMA loader on TMA-eligible shapes
@@ -121,12 +127,13 @@ class SelectiveScanFn(torch.autograd.Function):
         out = torch.empty((batch, dim, L), dtype=u.dtype, device=u.device)
         x = torch.empty((batch, dim, nchunks, N), dtype=torch.float32, device=u.device)
         desc = NzScanDesc()
-        _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC)
+        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC)
         desc.out = _ptr(out)
         desc.out_stride[0], desc.out_stride[1] = out.stride(0), out.stride(1)
         desc.x = _ptr(x)
         with torch.cuda.device(u.device):
             _native.check(lib.nz_scan_fwd(ctypes.byref(desc), _stream(u.device)), "nz_scan_fwd")
+        del ws
         ctx.delta_softplus = bool(delta_softplus)
         ctx.has_z = z is not None
         ctx.has_D = D is not None
@@ -153,14 +160,14 @@ class SelectiveScanFn(torch.autograd.Function):
         dz = torch.empty_like(du) if ctx.has_z else None
         dA = torch.zeros((dim, N), dtype=torch.float32, device=dev)
         dpg = dim // G
-        single_owner = dpg == (_ROWS_PER_CTA if dpg % _ROWS_PER_CTA == 0 else 1)
+        single_owner = dpg <= _ROWS_PER_TILE
         mk = torch.empty if single_owner else torch.zeros
         dB = mk((batch, G, N, L), dtype=torch.float32, device=dev)
         dC = mk((batch, G, N, L), dtype=torch.float32, device=dev)
         dD = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_D else None
         dbias = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_bias else None
         desc = NzScanDesc()
-        _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC)
+        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC)
         desc.x = _ptr(x)
         desc.dout = _ptr(dout)
         desc.dout_stride[0], desc.dout_stride[1] = dout.stride(0), dout.stride(1)
@@ -168,6 +175,7 @@ class SelectiveScanFn(torch.autograd.Function):
         desc.dA, desc.dB, desc.dC, desc.dD, desc.ddelta_bias = _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias)
         with torch.cuda.device(dev):
             _native.check(lib.nz_scan_bwd(ctypes.byref(desc), _stream(dev)), "nz_scan_bwd")
+        del ws
         if ctx.squeeze_B:  # :67-68
             dB = dB.squeeze(1)
         if ctx.squeeze_C:

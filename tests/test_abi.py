@@ -33,8 +33,12 @@ def test_struct_mirror_matches_the_compiled_layout():
     from nnuzoo_b200 import _native
     lib = _native.lib()  # raises if sizeof(NzScanDesc) or the ABI version disagree
     assert lib.nz_sizeof_scan_desc() == ctypes.sizeof(_native.NzScanDesc)
-    assert lib.nz_scan_num_chunks(1) == 1 and lib.nz_scan_num_chunks(257) == 2
-    assert lib.nz_scan_num_chunks(512 * 512) == 1024
+    ck = _native.NZ_CHUNK
+    assert lib.nz_scan_num_chunks(1) == 1 and lib.nz_scan_num_chunks(ck + 1) == 2
+    assert lib.nz_scan_num_chunks(512 * 512) == 512 * 512 // ck
+    d = _native.NzScanDesc()
+    d.batch, d.dim = 3, 40
+    assert lib.nz_scan_workspace_bytes(ctypes.byref(d)) == _native.workspace_bytes(3, 40)
 
 
 def test_invalid_descriptors_are_rejected_with_a_message():

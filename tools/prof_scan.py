@@ -39,7 +39,8 @@ def main():
     D = torch.ones(kd, device=dev)
     bias = torch.full((kd,), -2.0, device=dev)
     dA, dD, db = torch.zeros(kd, N, device=dev), torch.zeros(kd, device=dev), torch.zeros(kd, device=dev)
-    nch = (L + 255) // 256
+    nch = (L + _native.NZ_CHUNK - 1) // _native.NZ_CHUNK
+    ws = torch.empty(_native.workspace_bytes(batch, kd), dtype=torch.uint8, device=dev)
     x = torch.empty(batch * kd * nch * N, device=dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     st = torch.cuda.current_stream()
@@ -57,6 +58,7 @@ def main():
             s[0], s[1], s[2] = G * N * L, N * L, L
         d.A_stride = N
         d.out, d.x, d.du, d.ddelta = p(out), p(x), p(du), p(dd)
+        d.workspace, d.workspace_bytes = p(ws), _native.workspace_bytes(batch, kd)
         d.dA, d.dB, d.dC, d.dD, d.ddelta_bias = p(dA), p(dB), p(dC), p(dD), p(db)
         return d
 

@@ -15,7 +15,7 @@ SRCS = ["capi.cu", "cross_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", 
 
 def build(spec):
     name, _, defs = spec.partition(":")
-    flags = [d for d in defs.split(",") if d]
+    flags = [d for d in defs.split(",") if d] + ["-DNZ_F32_ONLY"]
     d = os.path.join(OUT, name)
     os.makedirs(d, exist_ok=True)
 
@@ -27,7 +27,7 @@ def build(spec):
             sys.stderr.write(r.stderr)
             raise SystemExit(f"{name}: nvcc failed on {src}")
         if src == "scan_inst_f32.cu":
-            regs = [l for l in r.stderr.splitlines() if "Li8ELb1ELb0" in l or "registers" in l or "spill" in l]
+            regs = [l for l in r.stderr.splitlines() if "Compiling entry" in l or "registers" in l or "spill" in l]
             with open(os.path.join(d, "ptxas_f32.txt"), "w") as f:
                 f.write("\n".join(regs))
         return obj
