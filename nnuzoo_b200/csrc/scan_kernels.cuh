@@ -37,7 +37,7 @@
 #include "nz_common.cuh"
 
 #ifndef NZ_BWD_KEEPB
-#define NZ_BWD_KEEPB 1  // 1: keep B_t[n] in registers instead of re-reading the tile for sum_n dh*B
+#define NZ_BWD_KEEPB 0  // 1: keep B_t[n] in registers instead of re-reading the tile for sum_n dh*B (costs 8 registers)
 #endif
 
 namespace nz {
@@ -62,6 +62,7 @@ struct alignas(64) ScanKArgs {
   int nck;        // checkpoints along L (ceil(L / kCkpt))
   int ntiles;     // nrb_total * nchunks
   int softplus;
+  int skew;      // states the later chunk's tile must be ahead before a dependent tile starts polling
   int vec_out;   // out rows 16-byte aligned -> vector stores
   int vec_grad;  // du/ddelta/dz and dB/dC rows 16-byte aligned
 };
@@ -82,9 +83,11 @@ struct ScanCfg {
   static constexpr int ROWS_REGION = ((ROWS_TX + 1023) / 1024) * 1024;
   static constexpr int BC_TX = 2 * BCTILE;                        // bytes per B/C stage
   static constexpr int SLROW = TL * 4;                            // one fp32 slab row
-  static constexpr int SLAB = kBwd ? WARPS * SLROW : 0;           // fp32 [WARPS][TL], rows of a warp pre-reduced
-  static constexpr int GSB = kBwd ? kMaxState * R * LPR * 4 : 0;  // per-lane dA partials [n][row][segment]
-  static constexpr int SMALL = 128 + (kBwd ? 2 : 1) * R * kMaxState * 4;
+  static constexpr int SLAB = kBwd ? R * SLROW : 0;               // fp32 [R][TL]: one array of one slab buffer
+  static constexpr int NRW = (2 * TL / 4) / 32;                   // warps reducing one state's dB + dC slabs
+  static constexpr int GSB = kBwd ? kMaxState * R * (LPR / 2) * 4 : 0;  // dA partials [n][row][segment pair]
+  static constexpr int SMALL = 128 + (kBwd ? 3 : 2) * R * kMaxState * 4;
+  static_assert(!kBwd || (NRW >= 1 && WARPS % NRW == 0), "reducer warps must tile the CTA");
   static_assert(RPW == 1 || RPW == 2, "one or two rows per warp");
   static_assert(TL % kCkpt == 0, "a tile is a whole number of checkpoint intervals");
   static_assert(!kBwd || TL == kCkpt, "the backward restarts from a checkpoint at every tile");
@@ -92,7 +95,7 @@ struct ScanCfg {
   static_assert(SEGB >= 16 && SEGB % 16 == 0, "a lane's segment must be whole 16-byte vectors");
   static_assert(M % 2 == 0, "packed fp32x2 math works on time pairs");
   static constexpr size_t smem_bytes(bool tma) {
-    return 1024 + (size_t)ROWS_REGION + (size_t)(tma ? 2 : 1) * BC_TX + 2 * (size_t)SLAB + (size_t)GSB + SMALL;
+    return 1024 + (size_t)ROWS_REGION + (size_t)(tma ? 2 : 1) * BC_TX + 5 * (size_t)SLAB + (size_t)GSB + SMALL;
   }
 };
 
@@ -223,6 +226,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] rows, [1],[2] B/C stages
   volatile int* tk = reinterpret_cast<volatile int*>(tail + 32);  // ring of 4 tickets
   float* sm_A2 = reinterpret_cast<float*>(tail + 128);
+  float* sm_hin = sm_A2 + R * kMaxState;  // h carried into the tile when the previous chunk had already finished
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sl = lane / RPW;                      // segment (time) index inside the row
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     if (t >= a.ntiles) break;
     const TileId q = decode_tile<R, false>(a, t);
     const int c = q.c, s = kTMA ? (k & 1) : 0;
-    const bool row_ok = rloc < q.rows_valid;
+    const bool row_ok = kTMA || rloc < q.rows_valid;  // the TMA path only runs whole row blocks
     const int d = q.d0 + (row_ok ? rloc : 0);
     const long rowg = (long)q.b * a.dim + d;
     unsigned nxt = 0;
@@ -279,19 +283,27 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
 
     const float Dv = a.D ? __ldg(a.D + d) : 0.f;
     const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
-    float a2pre[APT];
+    // per (row, state) tile constants, one per thread: A and -- if the previous chunk's tile has already
+    // published it -- the h carry (the common case when row blocks outnumber the CTAs; otherwise the
+    // state loop polls per state, see below)
+    float a2pre[APT], hpre[APT];
+    bool all_in = true;
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
       const int i = tid + j * NT, r = i / kMaxState, n = i % kMaxState;
-      a2pre[j] = (i < R * kMaxState && r < q.rows_valid && n < N) ? __ldg(a.A + (long)(q.d0 + r) * a.A_ds + n) * kLog2e : 0.f;
+      const bool ok = i < R * kMaxState && r < q.rows_valid && n < N;
+      a2pre[j] = ok ? __ldg(a.A + (long)(q.d0 + r) * a.A_ds + n) * kLog2e : 0.f;
+      hpre[j] = 0.f;
+      if (ok && c > 0) {
+        unsigned tag;
+        slot_load(a.carry + ((((long)q.b * a.dim + q.d0 + r) * 2 + ((c - 1) & 1)) * kMaxState + n), hpre[j], tag);
+        all_in = all_in && tag == (unsigned)c;
+      }
     }
-    // chained carry-in of state 0 (later states are prefetched one state ahead)
     const unsigned long long* cin = a.carry + (rowg * 2 + ((c - 1) & 1)) * kMaxState;
     unsigned long long* cout = a.carry + (rowg * 2 + (c & 1)) * kMaxState;
     const bool chained = c > 0 && row_ok;
-    float cv_next = 0.f;
-    unsigned ct_next = 0;
-    if (chained) slot_load(cin, cv_next, ct_next);
+    bool fast;  // every h carry of the tile was already there: no polling in the state loop
 
     if constexpr (kTMA) {
       mbar_wait(&bars[0], k & 1);
@@ -310,10 +322,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
                        kMaxState, ts, a.L);
 #pragma unroll
       for (int j = 0; j < APT; ++j)
-        if (tid + j * NT < R * kMaxState) sm_A2[tid + j * NT] = a2pre[j];
-      __syncthreads();
+        if (tid + j * NT < R * kMaxState) {
+          sm_A2[tid + j * NT] = a2pre[j];
+          sm_hin[tid + j * NT] = hpre[j];
+        }
+      fast = __syncthreads_and(all_in) != 0;
     }
     const long t0 = (long)c * TL + sl * M;
+    const int nvalid = (int)max(0L, min((long)M, a.L - t0));  // steps of this lane's segment inside the sequence
 
     float dlu[M], dl[M], y[M], zz[kHasZ ? M : 1];
     lds_seg<T, M, ROWB>(rows, rloc, lp, dlu);
@@ -324,7 +340,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     for (int i = 0; i < M; ++i) {
       float x = dl[i] + bias;
       if (a.softplus) x = softplus_f(x);
-      if (t0 + i >= a.L) x = 0.f;  // beyond the sequence: a = 1, b = 0 -> state passes through
+      if (i >= nvalid) x = 0.f;  // beyond the sequence: a = 1, b = 0 -> state passes through
       dl[i] = x;
       dlsum += x;
       y[i] = Dv * dlu[i];
@@ -333,9 +349,12 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     if constexpr (kTMA) {
 #pragma unroll
       for (int j = 0; j < APT; ++j)
-        if (tid + j * NT < R * kMaxState) sm_A2[tid + j * NT] = a2pre[j];
+        if (tid + j * NT < R * kMaxState) {
+          sm_A2[tid + j * NT] = a2pre[j];
+          sm_hin[tid + j * NT] = hpre[j];
+        }
       // the row values now live in registers: refill the row tiles for the next ticket
-      __syncthreads();
+      fast = __syncthreads_and(all_in) != 0;
       if (tid == 0) {
         const int tn = tk[(k + 1) & 3];
         if (tn < a.ntiles) issue_rows(decode_tile<R, false>(a, tn));
@@ -347,21 +366,43 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     T* outrow = reinterpret_cast<T*>(a.out) + (long)q.b * a.o_bs + (long)d * a.o_ds;
     float* xrow = a.x + rowg * (long)a.nck * N;
 
+    // when the previous chunk's tile is still running: start once it is a few states ahead, so that the
+    // one-state-ahead prefetch of the per-state polling finds its data
+    float cv_next = 0.f;
+    unsigned ct_next = 0;
+    if (!fast && chained) {
+      const int nsk = min(a.skew, N - 1);
+      unsigned tg;
+      float dummy;
+      do {
+        slot_load(cin + nsk, dummy, tg);
+      } while (tg != (unsigned)c);
+      slot_load(cin, cv_next, ct_next);
+    }
+
 #pragma unroll 1
     for (int n = 0; n < NP; n += NQ) {  // NQ independent states per trip (instruction-level parallelism)
       float hc[NQ], P[NQ], H[NQ];
       unsigned ctag[NQ];
       float av[NQ][M], bv[NQ][M];
-      // carry-in: state n was prefetched during the previous trip; fetch the others / the next one now
-      hc[0] = cv_next;
-      ctag[0] = ct_next;
+      if (fast) {
 #pragma unroll
-      for (int qi = 1; qi < NQ; ++qi) {
-        hc[qi] = 0.f;
-        ctag[qi] = 0;
-        if (chained) slot_load(cin + n + qi, hc[qi], ctag[qi]);
+        for (int qi = 0; qi < NQ; ++qi) {
+          hc[qi] = sm_hin[rloc * kMaxState + n + qi];
+          ctag[qi] = (unsigned)c;
+        }
+      } else {
+        // state n was prefetched during the previous trip; fetch the others / the next one now
+        hc[0] = cv_next;
+        ctag[0] = ct_next;
+#pragma unroll
+        for (int qi = 1; qi < NQ; ++qi) {
+          hc[qi] = 0.f;
+          ctag[qi] = 0;
+          if (chained) slot_load(cin + n + qi, hc[qi], ctag[qi]);
+        }
+        if (chained && n + NQ < NP) slot_load(cin + n + NQ, cv_next, ct_next);
       }
-      if (chained && n + NQ < NP) slot_load(cin + n + NQ, cv_next, ct_next);
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
         const float A2 = sm_A2[rloc * kMaxState + n + qi];
@@ -389,7 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         for (int qi = 0; qi < NQ; ++qi) ks_up_w(P[qi], H[qi], off * RPW);
       }
       // the chained carry must have arrived by now
-      if (chained) {
+      if (!fast && chained) {
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
           while (ctag[qi] != (unsigned)c) slot_load(cin + n + qi, hc[qi], ctag[qi]);
@@ -449,28 +490,38 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
 // ================================================================================================
 // Backward
 // ================================================================================================
+// 16-byte vector add to global memory (one RED per four floats)
+__device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 template <typename T, int M, int LPR, int WARPS, bool kTMA, bool kHasZ>
 __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     scan_bwd_kernel(const __grid_constant__ ScanKArgs a) {
   using Cfg = ScanCfg<T, M, LPR, WARPS, kHasZ, true>;
   constexpr int R = Cfg::R, TL = Cfg::TL, ROWB = Cfg::ROWB, SEGB = Cfg::SEGB, RPW = Cfg::RPW;
-  constexpr int ROWTILE = Cfg::ROWTILE, BCTILE = Cfg::BCTILE, SLROW = Cfg::SLROW;
+  constexpr int ROWTILE = Cfg::ROWTILE, BCTILE = Cfg::BCTILE, SLROW = Cfg::SLROW, SLAB = Cfg::SLAB;
   constexpr int NT = WARPS * 32;
   constexpr int H2 = M / 2;
   constexpr int APT = (R * kMaxState + NT - 1) / NT;
+  constexpr int NRW = Cfg::NRW;          // warps that reduce one state's slabs (one float4 of dB or dC per lane)
+  constexpr int NGRP = WARPS / NRW;      // the reducing warps rotate over the states
+  constexpr int QPA = TL / 4;            // float4 items per array
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* rows = smem;
   uint8_t* bcs = smem + Cfg::ROWS_REGION;
-  uint8_t* slabB = bcs + (kTMA ? 2 : 1) * Cfg::BC_TX;
-  uint8_t* slabC = slabB + Cfg::SLAB;
-  float* sm_gs = reinterpret_cast<float*>(slabC + Cfg::SLAB);  // [n][row][segment] dA partials of this tile
+  uint8_t* slabs = bcs + (kTMA ? 2 : 1) * Cfg::BC_TX;           // [2 buffers][dB, dC][R][TL] fp32
+  uint8_t* ucopy = slabs + 4 * SLAB;                            // [R][TL] fp32: the tile's u, re-read by the epilogue
+  float* sm_gs = reinterpret_cast<float*>(ucopy + SLAB);        // [n][row][segment pair] dA partials of this tile
   uint8_t* tail = reinterpret_cast<uint8_t*>(sm_gs) + Cfg::GSB;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // [0] rows, [1],[2] B/C stages, [3] slab full, [4] slab free
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // [0] rows, [1],[2] B/C stages, [3],[4] slab full, [5],[6] slab free
   volatile int* tk = reinterpret_cast<volatile int*>(tail + 64);
   float* sm_A2 = reinterpret_cast<float*>(tail + 128);
-  float* sm_hc = sm_A2 + R * kMaxState;  // h carried into the tile (forward checkpoints)
+  float* sm_hc = sm_A2 + R * kMaxState;   // h carried into the tile (forward checkpoints)
+  float* sm_dhc = sm_hc + R * kMaxState;  // dh carried into the tile when the later chunk had already finished
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sl = lane / RPW;
@@ -479,13 +530,15 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   const int N = a.dstate;
   const uint32_t segoff = sl * SEGB;
   const LanePre<M, T> lp(segoff);
-  // slab addressing (loop invariant).  Writers: the even lanes of a warp own the dB sums, the odd
-  // lanes the dC sums; the dC slab flips 16-byte-chunk bit 0 so the 8 lanes of a quarter warp (four
-  // segments x two slabs) land in 8 different bank groups.
+  // slab addressing (loop invariant): row = rloc, the lane's M floats.  Odd rows flip 16-byte-chunk
+  // bit 0 so that the 8 lanes of a quarter warp (four segments x two rows) hit 8 different bank groups.
   uint32_t slab_w[M / 4];
 #pragma unroll
-  for (int j = 0; j < M / 4; ++j)
-    slab_w[j] = (uint32_t)((RPW == 2 && rw) ? Cfg::SLAB : 0) + (swz128(warp * SLROW + sl * (M * 4) + 16 * j) ^ ((RPW == 2 && rw) ? 16u : 0u));
+  for (int j = 0; j < M / 4; ++j) slab_w[j] = swz128(rloc * SLROW + sl * (M * 4) + 16 * j) ^ ((rloc & 1) ? 16u : 0u);
+  // reducer role: lane -> one float4 (four time steps) of dB (red_arr 0) or dC (1)
+  const int red_item = (warp % NRW) * 32 + lane;
+  const int red_arr = red_item / QPA, red_q = red_item % QPA;
+  const uint32_t red_in = swz128((uint32_t)red_q * 16u);
 
   auto issue_rows = [&](const TileId& q) {
     mbar_arrive_expect_tx(&bars[0], Cfg::ROWS_TX);
@@ -509,6 +562,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], NT);
     mbar_init(&bars[4], NT);
+    mbar_init(&bars[5], NRW * 32);
+    mbar_init(&bars[6], NRW * 32);
     fence_mbar_init();
     const int t0 = (int)atomicAdd(a.ticket, 1u), t1 = (int)atomicAdd(a.ticket, 1u);
     tk[0] = t0;
@@ -524,29 +579,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   }
   __syncthreads();
 
-  // slab reduction work items of this thread: element `red_t` of dB (red_arr 0) or dC (1)
-  constexpr int NRED = (2 * TL + NT - 1) / NT;
-  static_assert((SLROW & (SLROW - 1)) == 0 && SLROW <= 1024, "slab rows: power-of-two pitch <= 1024 bytes");
-  bool red_ok[NRED];
-  int red_arr[NRED], red_t[NRED];
-  uint32_t red_base[NRED], red_in[NRED];  // slab offset; swizzled in-row offset (dC slab: chunk bit 0 flipped, see slab_w)
-#pragma unroll
-  for (int j = 0; j < NRED; ++j) {
-    const int item = tid + j * NT;
-    red_ok[j] = item < 2 * TL;
-    red_arr[j] = item / TL;
-    red_t[j] = item - red_arr[j] * TL;
-    red_base[j] = red_arr[j] ? (uint32_t)Cfg::SLAB : 0u;
-    red_in[j] = swz128((uint32_t)red_t[j] * 4u) ^ (red_arr[j] && RPW == 2 ? 16u : 0u);
-  }
-  unsigned gtrip = 0;  // states processed so far (parity of the slab hand-off barriers)
+  unsigned g = 0;  // states processed so far by this CTA: slab buffer g & 1, barrier parity (g >> 1) & 1
 
   for (int k = 0;; ++k) {
     const int t = tk[k & 3];
     if (t >= a.ntiles) break;
     const TileId q = decode_tile<R, true>(a, t);
     const int c = q.c, s = kTMA ? (k & 1) : 0;
-    const bool row_ok = rloc < q.rows_valid;
+    const bool row_ok = kTMA || rloc < q.rows_valid;  // the TMA path only runs whole row blocks
     const int d = q.d0 + (row_ok ? rloc : 0);
     const long rowg = (long)q.b * a.dim + d;
     const int bpg = a.nrb;
@@ -555,13 +595,23 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
 
     const float Dv = a.D ? __ldg(a.D + d) : 0.f;
     const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
-    float a2pre[APT], hcpre[APT];
+    // per (row, state) tile constants, one per thread: A, the h checkpoint, and -- if the tile of the
+    // later chunk has already published it -- the dh carry (the common case when row blocks outnumber
+    // the CTAs; otherwise the state loop polls per state, see below)
+    float a2pre[APT], hcpre[APT], dhpre[APT];
+    bool all_in = true;
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
       const int i = tid + j * NT, r = i / kMaxState, n = i % kMaxState;
       const bool ok = i < R * kMaxState && r < q.rows_valid && n < N;
       a2pre[j] = ok ? __ldg(a.A + (long)(q.d0 + r) * a.A_ds + n) * kLog2e : 0.f;
       hcpre[j] = (ok && c > 0) ? __ldg(a.x + (((long)q.b * a.dim + q.d0 + r) * a.nck + (c - 1)) * N + n) : 0.f;
+      dhpre[j] = 0.f;
+      if (ok && c + 1 < a.nchunks) {
+        unsigned tag;
+        slot_load(a.carry + ((((long)q.b * a.dim + q.d0 + r) * 2 + ((c + 1) & 1)) * kMaxState + n), dhpre[j], tag);
+        all_in = all_in && tag == (unsigned)c + 2u;
+      }
     }
     // dl of the first step of the later chunk (a_{t+1} of the reverse recurrence at the tile end)
     float dlfirst_next = 0.f;
@@ -570,14 +620,11 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       if (a.softplus) x = softplus_f(x);
       dlfirst_next = x;
     }
-    // chained dh carry-in of state 0 (published by the tile of chunk c+1)
     const unsigned long long* cin = a.carry + (rowg * 2 + ((c + 1) & 1)) * kMaxState;
     unsigned long long* cout = a.carry + (rowg * 2 + (c & 1)) * kMaxState;
     const bool chained = c + 1 < a.nchunks && row_ok;
-    float cv_next = 0.f;
-    unsigned ct_next = 0;
-    if (chained) slot_load(cin, cv_next, ct_next);
 
+    bool fast;  // every dh carry of the tile was already there: no polling in the state loop
     if constexpr (kTMA) {
       mbar_wait(&bars[0], k & 1);
     } else {
@@ -600,15 +647,21 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         if (tid + j * NT < R * kMaxState) {
           sm_A2[tid + j * NT] = a2pre[j];
           sm_hc[tid + j * NT] = hcpre[j];
+          sm_dhc[tid + j * NT] = dhpre[j];
         }
-      __syncthreads();
+      fast = __syncthreads_and(all_in) != 0;
     }
     const long t0 = (long)c * TL + sl * M;
+    const int nvalid = (int)max(0L, min((long)M, a.L - t0));  // steps of this lane's segment inside the sequence
 
-    float uu[M], dl[M], dy[M], dlu[M], sB[M], ddl[M];
+    float dl[M], dy[M], dlu[M], sB[M], ddl[M];
     float yv[kHasZ ? M : 1], dzf[kHasZ ? M : 1];
-    lds_seg<T, M, ROWB>(rows, rloc, lp, uu);
+    lds_seg<T, M, ROWB>(rows, rloc, lp, dlu);
     lds_seg<T, M, ROWB>(rows + ROWTILE, rloc, lp, dl);
+    // u is needed again only by the epilogue: park it in shared memory (the row tiles are refilled early)
+#pragma unroll
+    for (int j = 0; j < M / 4; ++j)
+      *reinterpret_cast<float4*>(ucopy + slab_w[j]) = make_float4(dlu[4 * j], dlu[4 * j + 1], dlu[4 * j + 2], dlu[4 * j + 3]);
     lds_seg<T, M, ROWB>(rows + 2 * ROWTILE, rloc, lp, dy);
     if constexpr (kHasZ) {
       float zz[M];
@@ -618,7 +671,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         const float sg = sigmoid_f(zz[i]);
         dzf[i] = dy[i] * sg * (1.f + zz[i] * (1.f - sg));  // dout * d silu(z)/dz
         dy[i] = dy[i] * zz[i] * sg;                         // dout * silu(z)
-        yv[i] = Dv * uu[i];
+        yv[i] = Dv * dlu[i];
       }
     }
     float dlsum = 0.f;
@@ -626,13 +679,13 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     for (int i = 0; i < M; ++i) {
       float x = dl[i] + bias;
       if (a.softplus) x = softplus_f(x);
-      if (t0 + i >= a.L) {
+      if (i >= nvalid) {
         x = 0.f;
         dy[i] = 0.f;
       }
       dl[i] = x;
       dlsum += x;
-      dlu[i] = x * uu[i];
+      dlu[i] = x * dlu[i];
       sB[i] = 0.f;
       ddl[i] = 0.f;
     }
@@ -648,8 +701,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         if (tid + j * NT < R * kMaxState) {
           sm_A2[tid + j * NT] = a2pre[j];
           sm_hc[tid + j * NT] = hcpre[j];
+          sm_dhc[tid + j * NT] = dhpre[j];
         }
-      __syncthreads();  // row values are in registers: refill the row tiles for the next ticket
+      fast = __syncthreads_and(all_in) != 0;  // row values are in registers: refill the row tiles for the next ticket
       if (tid == 0) {
         const int tn = tk[(k + 1) & 3];
         if (tn < a.ntiles) issue_rows(decode_tile<R, true>(a, tn));
@@ -658,34 +712,67 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     }
     const uint8_t* tB = bcs + s * Cfg::BC_TX;
     const uint8_t* tC = tB + BCTILE;
-    float* dBg = a.dB + (((long)q.b * a.ngroups + q.g) * N) * a.L + (long)c * TL;
-    float* dCg = a.dC + (((long)q.b * a.ngroups + q.g) * N) * a.L + (long)c * TL;
+    float* dG = (red_arr ? a.dC : a.dB) + (((long)q.b * a.ngroups + q.g) * N) * a.L + (long)c * TL + red_q * 4;
+    const bool red_vec = a.vec_grad && (long)c * TL + red_q * 4 + 4 <= a.L;
 
-    auto reduce_slabs = [&](int n) {  // dB/dC of state n: sum the per-warp slab rows, add to global
+    // dB/dC of state n (CTA-local state counter gp): the NRW reducing warps add the R slab rows
+    auto reduce_slab = [&](int n, unsigned gp) {
+      const int bq = gp & 1;
+      mbar_wait(&bars[3 + bq], (gp >> 1) & 1);
+      const uint8_t* sb = slabs + (bq * 2 + red_arr) * SLAB;
+      float2 lo = f2(0.f, 0.f), hi = f2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < NRED; ++j) {
-        if (red_ok[j]) {
-          float acc = 0.f;
+      for (int r = 0; r < R; ++r) {  // row r adds r*SLROW to the address and its swizzle key / parity flip to the offset
+        const uint32_t key = (uint32_t)((((r * (SLROW / 128)) & 7) << 4) ^ ((r & 1) ? 16 : 0));
+        const float4 v = *reinterpret_cast<const float4*>(sb + r * SLROW + (red_in ^ key));
+        lo = __fadd2_rn(lo, f2(v.x, v.y));
+        hi = __fadd2_rn(hi, f2(v.z, v.w));
+      }
+      mbar_arrive(&bars[5 + bq]);
+      float* dst = dG + (long)n * a.L;
+      if (red_vec) {
+        if (bpg == 1)
+          *reinterpret_cast<float4*>(dst) = make_float4(lo.x, lo.y, hi.x, hi.y);
+        else
+          red_add_v4(dst, make_float4(lo.x, lo.y, hi.x, hi.y));
+      } else {
+        const float vv[4] = {lo.x, lo.y, hi.x, hi.y};
+        const long tg = (long)c * TL + red_q * 4;
 #pragma unroll
-          for (int w = 0; w < WARPS; ++w)  // row w adds w*SLROW to the address and (w*SLROW/128)&7 to the swizzle key
-            acc += *reinterpret_cast<const float*>(slabB + red_base[j] + w * SLROW +
-                                                   (red_in[j] ^ (uint32_t)(((w * (SLROW / 128)) & 7) << 4)));
-          if (red_t[j] + (long)c * TL < a.L) {
-            float* dst = (red_arr[j] ? dCg : dBg) + (long)n * a.L + red_t[j];
-            if (bpg == 1) *dst = acc; else atomicAdd(dst, acc);
+        for (int e = 0; e < 4; ++e)
+          if (tg + e < a.L) {
+            if (bpg == 1) dst[e] = vv[e]; else atomicAdd(dst + e, vv[e]);
           }
-        }
       }
     };
 
+    // when the later chunk's tile is still running: start once it is a few states ahead, so that the
+    // one-state-ahead prefetch of the per-state polling below finds its data
+    float cv_next = 0.f;
+    unsigned ct_next = 0;
+    if (!fast && chained) {
+      const int nsk = min(a.skew, N - 1);
+      unsigned tg;
+      float dummy;
+      do {
+        slot_load(cin + nsk, dummy, tg);
+      } while (tg != (unsigned)c + 2u);
+      slot_load(cin, cv_next, ct_next);
+    }
+    float* gsp = sm_gs + rloc * (LPR / 2) + (sl >> 1);
+
 #pragma unroll 1
-    for (int n = 0; n < N; ++n) {
+    for (int n = 0; n < N; ++n, ++g) {
       const float A2 = sm_A2[rloc * kMaxState + n];
       const float An = A2 * kLn2;
       const float hc = sm_hc[rloc * kMaxState + n];
-      float dhc = cv_next;
-      unsigned dtag = ct_next;
-      if (chained && n + 1 < N) slot_load(cin + n + 1, cv_next, ct_next);
+      float dhc = sm_dhc[rloc * kMaxState + n];
+      unsigned dtag = 0;
+      if (!fast) {
+        dhc = cv_next;
+        dtag = ct_next;
+        if (chained && n + 1 < N) slot_load(cin + n + 1, cv_next, ct_next);
+      }
       float av[M], bv[M], cv[M], hh[M];
       [[maybe_unused]] float Bk[M];
       lds_seg<T, M, ROWB>(tB, n, lp, bv);
@@ -724,17 +811,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         ks_up_w(P, H, off * RPW);
         ks_down_w(Q, G, off * RPW);
       }
-      if (chained) {
+      if (!fast && chained) {
         while (dtag != (unsigned)c + 2u) slot_load(cin + n, dhc, dtag);
       }
       float h = ks_enter_up_w<RPW>(P, H, hc);
       float dh = ks_enter_down_w<RPW>(Q, G, dhc);
       if (sl == 0 && row_ok) slot_store(cout + n, fmaf(Q, dhc, G), (unsigned)c + 1u);  // dh leaving the tile
-      if (n > 0) {  // reduce the previous state's slab while this state's scans are in flight
-        mbar_wait(&bars[3], (gtrip - 1) & 1);
-        reduce_slabs(n - 1);
-        mbar_arrive(&bars[4]);
-      }
+      // the reducing warps of the previous state add its slabs while this state's scans are in flight
+      if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
       // ---- replay both recurrences with the true carries ----
       float dd[M];
 #pragma unroll
@@ -797,38 +881,26 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         }
       }
       // this lane's share of dA[n]: summed over the segments at the end of the tile
-      sm_gs[(n * R + rloc) * LPR + sl] = gs2.x + gs2.y;
+      {
+        const float gsl = gs2.x + gs2.y;
+        const float gsum = gsl + __shfl_down_sync(0xffffffffu, gsl, RPW);  // this segment + the next one
+        if ((sl & 1) == 0) gsp[n * (R * LPR / 2)] = gsum;
+      }
 
-      // ---- dB/dC: add the rows of this warp (one shuffle per value), hand the sums to the slabs ----
-      // slab(n) is reduced by everybody during state n+1 (after its scans), so both waits sit far
-      // behind the matching arrives.
-      if constexpr (RPW == 2) {
-        float red[M];
-#pragma unroll
-        for (int i = 0; i < M; ++i) {
-          const float send = rw ? vB[i] : vC[i];
-          const float keep = rw ? vC[i] : vB[i];
-          red[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-        }
-        if (gtrip > 0) mbar_wait(&bars[4], (gtrip - 1) & 1);  // slab(n-1) has been consumed
-#pragma unroll
-        for (int j = 0; j < M / 4; ++j)
-          *reinterpret_cast<float4*>(slabB + slab_w[j]) = make_float4(red[4 * j], red[4 * j + 1], red[4 * j + 2], red[4 * j + 3]);
-      } else {
-        if (gtrip > 0) mbar_wait(&bars[4], (gtrip - 1) & 1);
+      // ---- dB/dC: every row writes its products into slab buffer g & 1 (reduced two states later at the latest) ----
+      if (g >= 2) mbar_wait(&bars[5 + (g & 1)], ((g >> 1) - 1) & 1);  // the buffer's previous content has been consumed
+      {
+        uint8_t* sb = slabs + (g & 1) * (2 * SLAB);
 #pragma unroll
         for (int j = 0; j < M / 4; ++j) {
-          *reinterpret_cast<float4*>(slabC + slab_w[j]) = make_float4(vC[4 * j], vC[4 * j + 1], vC[4 * j + 2], vC[4 * j + 3]);
-          *reinterpret_cast<float4*>(slabB + slab_w[j]) = make_float4(vB[4 * j], vB[4 * j + 1], vB[4 * j + 2], vB[4 * j + 3]);
+          *reinterpret_cast<float4*>(sb + slab_w[j]) = make_float4(vB[4 * j], vB[4 * j + 1], vB[4 * j + 2], vB[4 * j + 3]);
+          *reinterpret_cast<float4*>(sb + SLAB + slab_w[j]) = make_float4(vC[4 * j], vC[4 * j + 1], vC[4 * j + 2], vC[4 * j + 3]);
         }
       }
-      mbar_arrive(&bars[3]);  // my part of slab(n) is written
-      ++gtrip;
+      mbar_arrive(&bars[3 + (g & 1)]);  // my part of slab(n) is written
     }
-    // the last state's slab of this tile
-    mbar_wait(&bars[3], (gtrip - 1) & 1);
-    reduce_slabs(N - 1);
-    mbar_arrive(&bars[4]);
+    // the last state's slabs of this tile
+    if ((int)((g - 1) % NGRP) == warp / NRW) reduce_slab(N - 1, g - 1);
 
     // ---- per-(row, t) epilogue ----
     const long rowlin = rowg * a.L;  // gradients are contiguous (batch, dim, L)
@@ -837,12 +909,18 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     for (int i = 0; i < M; ++i) outv[i] = fmaf(dl[i], sB[i], Dv * dy[i]);  // du
     if (row_ok) stg_items<T, M>(reinterpret_cast<T*>(a.du) + rowlin, outv, t0, a.L, a.vec_grad != 0);
     float dD_acc = 0.f, db_acc = 0.f;
+    float uu[M];
+#pragma unroll
+    for (int j = 0; j < M / 4; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(ucopy + slab_w[j]);
+      uu[4 * j] = v.x, uu[4 * j + 1] = v.y, uu[4 * j + 2] = v.z, uu[4 * j + 3] = v.w;
+    }
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       float gd = fmaf(uu[i], sB[i], ddl[i]);  // d loss / d dl
       // d softplus(x)/dx = sigmoid(x) = 1 - exp(-softplus(x))
       if (a.softplus) gd *= sigmoid_from_softplus(dl[i]);
-      if (t0 + i >= a.L) gd = 0.f;
+      if (i >= nvalid) gd = 0.f;
       outv[i] = gd;
       db_acc += gd;
       dD_acc = fmaf(dy[i], uu[i], dD_acc);
@@ -864,7 +942,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       if (a.dbias) atomicAdd(a.dbias + d, db_acc);
     }
 
-    // every warp is done with this tile's B/C stage, sm_A2 / sm_hc and has written its dA partials
+    // every warp is done with this tile's B/C stage, sm_A2 / sm_hc / sm_dhc and has written its dA partials
     __syncthreads();
     if (tid == 0) {
       tk[(k + 2) & 3] = (int)nxt;
@@ -874,11 +952,11 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     for (int j = 0; j < APT; ++j) {
       const int i = tid + j * NT, r = i % R, n = i / R;  // consecutive threads: consecutive rows (64-byte pitch)
       if (i < R * kMaxState && r < q.rows_valid && n < N) {
-        const float4* p = reinterpret_cast<const float4*>(sm_gs + (n * R + r) * LPR);
+        const float4* p = reinterpret_cast<const float4*>(sm_gs + (n * R + r) * (LPR / 2));
         float acc = 0.f;
 #pragma unroll
-        for (int v = 0; v < LPR / 4; ++v) {
-          const float4 w4 = p[(v + (r >> 1)) & (LPR / 4 - 1)];  // rotated: a quarter warp covers all 8 bank groups
+        for (int v = 0; v < LPR / 8; ++v) {
+          const float4 w4 = p[(v + (r >> 2)) & (LPR / 8 - 1)];  // rotated: a quarter warp covers all 8 bank groups
           acc += (w4.x + w4.y) + (w4.z + w4.w);
         }
         atomicAdd(a.dA + (long)(q.d0 + r) * N + n, acc);
