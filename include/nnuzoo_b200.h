@@ -159,6 +159,10 @@ int nz_set_device(int device);
 /* sizeof(NzScanDesc) as compiled into the library (lets FFI bindings verify their struct mirror) */
 int64_t nz_sizeof_scan_desc(void);
 
+/* Tools only: when non-NULL, forward launches write 6 u64 words per tile (ticket, SM, start / loop /
+ * wait / end times in ns) into this device buffer (tools/trace_tiles.py).  NULL switches it off. */
+void nz_debug_set_trace(void* device_buffer);
+
 const char* nz_last_error(void);
 int nz_abi_version(void);
 /* number of kernel launches this library has issued in the calling process (bench.py gpu_launches) */

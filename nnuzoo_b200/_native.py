@@ -83,6 +83,8 @@ def lib():
                 L.nz_set_device.restype = ctypes.c_int
                 L.nz_launch_count.restype = _i64
                 L.nz_sizeof_scan_desc.restype = _i64
+                L.nz_debug_set_trace.argtypes = [_vp]
+                L.nz_debug_set_trace.restype = None
                 if L.nz_sizeof_scan_desc() != ctypes.sizeof(NzScanDesc):
                     raise NativeLibraryError("NzScanDesc layout differs between _native.py and the .so")
                 if L.nz_abi_version() != ABI_VERSION:

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/nnuzoo_b200.h"
@@ -120,8 +121,11 @@ static int validate(const NzScanDesc* d, bool bwd) {
   return NZ_OK;
 }
 
+static void* g_trace = nullptr;  // tools only: see nz_debug_set_trace
+
 static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   memset(&a, 0, sizeof(a));
+  a.trace = bwd ? nullptr : reinterpret_cast<unsigned long long*>(g_trace);
   a.u = d->u; a.delta = d->delta; a.z = d->z; a.dout = d->dout; a.B = d->B; a.C = d->C;
   a.A = d->A; a.D = d->D; a.bias = d->delta_bias;
   a.out = d->out; a.du = d->du; a.ddelta = d->ddelta; a.dz = d->dz;
@@ -146,6 +150,7 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   // a dependent tile whose predecessor is still running starts `skew` states behind it; fewer row
   // blocks than CTAs means deeper pipelines along L, which want a smaller skew
   a.skew = a.nrb_total >= 64 ? 3 : (a.nrb_total >= 24 ? 2 : 1);
+  if (const char* e = getenv("NZ_SKEW")) a.skew = atoi(e);  // tuning override
   a.ticket = reinterpret_cast<unsigned*>(d->workspace);
   a.carry = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d->workspace) + kWsHeader);
   a.softplus = d->delta_softplus;
@@ -235,6 +240,8 @@ int nz_set_device(int device) {
 }
 
 int64_t nz_launch_count(void) { return (int64_t)nz::g_launches.load(); }
+
+void nz_debug_set_trace(void* device_buffer) { nz::g_trace = device_buffer; }
 
 // ------------------------------------------------------------------------------------------------
 // Host-buffer entry point: stage H2D, run forward (+ backward), copy results D2H.

@@ -52,6 +52,7 @@ struct alignas(64) ScanKArgs {
   float *x, *dA, *dB, *dC, *dD, *dbias;
   unsigned long long* carry;  // [batch*dim][2][16] {value, tag} slots of the chained hand-off
   unsigned* ticket;           // dynamic tile counter (zeroed by the host before the launch)
+  unsigned long long* trace;  // optional (tools only): 6 words per tile {ticket, smid, t_start, t_loop, wait, t_end} in ns
   long L;
   long u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, o_bs, o_ds, do_bs, do_ds;
   long B_bs, B_gs, B_ns, C_bs, C_gs, C_ns, A_ds;
@@ -104,6 +105,17 @@ __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, f2(-b.x, -b.y)); }
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned smid() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+  return r;
+}
 
 // ---- chained hand-off slots ----
 __device__ __forceinline__ void slot_store(unsigned long long* p, float v, unsigned tag) {
@@ -256,16 +268,12 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
     fence_mbar_init();
-    const int t0 = (int)atomicAdd(a.ticket, 1u), t1 = (int)atomicAdd(a.ticket, 1u);
+    const int t0 = (int)atomicAdd(a.ticket, 1u);
     tk[0] = t0;
-    tk[1] = t1;
-    if (kTMA) {
-      if (t0 < a.ntiles) {
-        const TileId q = decode_tile<R, false>(a, t0);
-        issue_rows(q);
-        issue_bc(q, 0);
-      }
-      if (t1 < a.ntiles) issue_bc(decode_tile<R, false>(a, t1), 1);
+    if (kTMA && t0 < a.ntiles) {
+      const TileId q = decode_tile<R, false>(a, t0);
+      issue_rows(q);
+      issue_bc(q, 0);
     }
   }
   __syncthreads();
@@ -278,8 +286,13 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     const bool row_ok = kTMA || rloc < q.rows_valid;  // the TMA path only runs whole row blocks
     const int d = q.d0 + (row_ok ? rloc : 0);
     const long rowg = (long)q.b * a.dim + d;
+    // Claim the NEXT ticket now (one tile ahead, not two: tiles then start in ticket order up to the
+    // spread of one tile duration, so a tile's predecessor along L is almost always already running);
+    // its B/C stage is free, its row tiles are requested once this tile's rows sit in registers.
     unsigned nxt = 0;
-    if (tid == 0) nxt = atomicAdd(a.ticket, 1u);  // ticket k+2; only needed at the end of this tile
+    if (tid == 0) nxt = atomicAdd(a.ticket, 1u);
+    unsigned long long tr_start = 0, tr_loop = 0, tr_wait = 0;
+    if (a.trace && tid == 0) tr_start = gtime_ns();
 
     const float Dv = a.D ? __ldg(a.D + d) : 0.f;
     const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
@@ -326,6 +339,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sm_A2[tid + j * NT] = a2pre[j];
           sm_hin[tid + j * NT] = hpre[j];
         }
+      if (tid == 0) tk[(k + 1) & 3] = (int)nxt;
       fast = __syncthreads_and(all_in) != 0;
     }
     const long t0 = (long)c * TL + sl * M;
@@ -353,11 +367,15 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sm_A2[tid + j * NT] = a2pre[j];
           sm_hin[tid + j * NT] = hpre[j];
         }
-      // the row values now live in registers: refill the row tiles for the next ticket
+      // the row values now live in registers: request the next ticket's tiles (rows + the free B/C stage)
       fast = __syncthreads_and(all_in) != 0;
       if (tid == 0) {
-        const int tn = tk[(k + 1) & 3];
-        if (tn < a.ntiles) issue_rows(decode_tile<R, false>(a, tn));
+        tk[(k + 1) & 3] = (int)nxt;
+        if ((int)nxt < a.ntiles) {
+          const TileId qn = decode_tile<R, false>(a, (int)nxt);
+          issue_rows(qn);
+          issue_bc(qn, (k + 1) & 1);
+        }
       }
       mbar_wait(&bars[1 + s], (k >> 1) & 1);
     }
@@ -380,6 +398,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       slot_load(cin, cv_next, ct_next);
     }
 
+    if (a.trace && tid == 0) tr_loop = gtime_ns();
 #pragma unroll 1
     for (int n = 0; n < NP; n += NQ) {  // NQ independent states per trip (instruction-level parallelism)
       float hc[NQ], P[NQ], H[NQ];
@@ -431,10 +450,12 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       }
       // the chained carry must have arrived by now
       if (!fast && chained) {
+        const unsigned long long w0 = (a.trace && tid == 0) ? gtime_ns() : 0;
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
           while (ctag[qi] != (unsigned)c) slot_load(cin + n + qi, hc[qi], ctag[qi]);
         }
+        if (a.trace && tid == 0) tr_wait += gtime_ns() - w0;
       }
       float h[NQ];
 #pragma unroll
@@ -476,13 +497,18 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       for (int i = 0; i < M; ++i) y[i] *= zz[i] * sigmoid_f(zz[i]);
     }
     if (row_ok) stg_items<T, M>(outrow, y, t0, a.L, a.vec_out != 0);
-
-    // every warp is done with this tile's B/C stage (and with sm_A2): refill it for ticket k + 2
-    __syncthreads();
-    if (tid == 0) {
-      tk[(k + 2) & 3] = (int)nxt;
-      if (kTMA && (int)nxt < a.ntiles) issue_bc(decode_tile<R, false>(a, (int)nxt), s);
+    if (a.trace && tid == 0) {
+      unsigned long long* tr = a.trace + (long)t * 6;
+      tr[0] = (unsigned long long)t | ((unsigned long long)fast << 32);
+      tr[1] = smid();
+      tr[2] = tr_start;
+      tr[3] = tr_loop;
+      tr[4] = tr_wait;
+      tr[5] = gtime_ns();
     }
+
+    // every warp is done with this tile's B/C stage, sm_A2 and sm_hin
+    __syncthreads();
     if (!kTMA) __syncthreads();
   }
 }
@@ -565,16 +591,12 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     mbar_init(&bars[5], NRW * 32);
     mbar_init(&bars[6], NRW * 32);
     fence_mbar_init();
-    const int t0 = (int)atomicAdd(a.ticket, 1u), t1 = (int)atomicAdd(a.ticket, 1u);
+    const int t0 = (int)atomicAdd(a.ticket, 1u);
     tk[0] = t0;
-    tk[1] = t1;
-    if (kTMA) {
-      if (t0 < a.ntiles) {
-        const TileId q = decode_tile<R, true>(a, t0);
-        issue_rows(q);
-        issue_bc(q, 0);
-      }
-      if (t1 < a.ntiles) issue_bc(decode_tile<R, true>(a, t1), 1);
+    if (kTMA && t0 < a.ntiles) {
+      const TileId q = decode_tile<R, true>(a, t0);
+      issue_rows(q);
+      issue_bc(q, 0);
     }
   }
   __syncthreads();
@@ -590,7 +612,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     const int d = q.d0 + (row_ok ? rloc : 0);
     const long rowg = (long)q.b * a.dim + d;
     const int bpg = a.nrb;
-    unsigned nxt = 0;
+    unsigned nxt = 0;  // the next ticket, claimed one tile ahead (see the forward kernel)
     if (tid == 0) nxt = atomicAdd(a.ticket, 1u);
 
     const float Dv = a.D ? __ldg(a.D + d) : 0.f;
@@ -649,6 +671,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sm_hc[tid + j * NT] = hcpre[j];
           sm_dhc[tid + j * NT] = dhpre[j];
         }
+      if (tid == 0) tk[(k + 1) & 3] = (int)nxt;
       fast = __syncthreads_and(all_in) != 0;
     }
     const long t0 = (long)c * TL + sl * M;
@@ -703,10 +726,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sm_hc[tid + j * NT] = hcpre[j];
           sm_dhc[tid + j * NT] = dhpre[j];
         }
-      fast = __syncthreads_and(all_in) != 0;  // row values are in registers: refill the row tiles for the next ticket
+      fast = __syncthreads_and(all_in) != 0;  // row values are in registers: request the next ticket's tiles
       if (tid == 0) {
-        const int tn = tk[(k + 1) & 3];
-        if (tn < a.ntiles) issue_rows(decode_tile<R, true>(a, tn));
+        tk[(k + 1) & 3] = (int)nxt;
+        if ((int)nxt < a.ntiles) {
+          const TileId qn = decode_tile<R, true>(a, (int)nxt);
+          issue_rows(qn);
+          issue_bc(qn, (k + 1) & 1);
+        }
       }
       mbar_wait(&bars[1 + s], (k >> 1) & 1);
     }
@@ -944,10 +971,6 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
 
     // every warp is done with this tile's B/C stage, sm_A2 / sm_hc / sm_dhc and has written its dA partials
     __syncthreads();
-    if (tid == 0) {
-      tk[(k + 2) & 3] = (int)nxt;
-      if (kTMA && (int)nxt < a.ntiles) issue_bc(decode_tile<R, true>(a, (int)nxt), s);
-    }
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
       const int i = tid + j * NT, r = i % R, n = i / R;  // consecutive threads: consecutive rows (64-byte pitch)
