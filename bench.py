@@ -98,6 +98,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def traffic_per_launch():
+    """Average DRAM bytes (read + write) per scan_bwd launch of this workload, from the committed ncu
+    capture of the same command (profiles/r01_bwd_traffic.json, written by tools/ncu_traffic.py)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_bwd_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -414,9 +424,11 @@ def run_gpu_arm(args):
             "patches_per_s_scan_only": world * BATCH / (ms_per_step * 1e-3),
             "frac_of_hbm_peak": value / world / peak,
             "roofline": {"bound": "hbm", "achieved": bwd_gbps, "peak": peak, "unit": "GB/s", "frac": bwd_gbps / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "kernel": "nz::scan_bwd_kernel<float,8,32,8,TMA> (all 80 launches per step; "
-                                   "algorithmic bytes 4*(5E+4S) per launch)",
+                         "traffic": traffic_per_launch(), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": wl.bwd_bytes / len(wl.scans),
+                         "kernel": "nz::scan_bwd_kernel<float, M=8, LPR=16, WARPS=8, TMA> (persistent tiles of 16 rows x "
+                                   "128 steps; all 80 launches per step; algorithmic bytes 4*(5E+4S) per launch, "
+                                   "achieved = sum of bytes / sum of CUDA-event durations of those launches)",
                          "share_of_step": bwd_ms / (ms_per_step * args.steps)},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

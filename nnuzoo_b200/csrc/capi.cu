@@ -149,7 +149,7 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   a.ntiles = a.nrb_total * a.nchunks;
   // a dependent tile whose predecessor is still running starts `skew` states behind it; fewer row
   // blocks than CTAs means deeper pipelines along L, which want a smaller skew
-  a.skew = a.nrb_total >= 64 ? 3 : (a.nrb_total >= 24 ? 2 : 1);
+  a.skew = a.nrb_total >= 24 ? 1 : 0;
   if (const char* e = getenv("NZ_SKEW")) a.skew = atoi(e);  // tuning override
   a.ticket = reinterpret_cast<unsigned*>(d->workspace);
   a.carry = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d->workspace) + kWsHeader);

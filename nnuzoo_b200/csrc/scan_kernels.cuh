@@ -36,6 +36,14 @@
 
 #include "nz_common.cuh"
 
+#ifndef NZ_FWD_UNROLL
+#define NZ_FWD_UNROLL 2  // measured: 2.73 vs 2.83 clk/elt/SM (profiles/r01_kernel_tuning.md)
+#endif
+#ifndef NZ_BWD_UNROLL
+#define NZ_BWD_UNROLL 1
+#endif
+#define NZ_PRAGMA_(x) _Pragma(#x)
+#define NZ_UNROLL(n) NZ_PRAGMA_(unroll n)
 #ifndef NZ_BWD_KEEPB
 #define NZ_BWD_KEEPB 0  // 1: keep B_t[n] in registers instead of re-reading the tile for sum_n dh*B (costs 8 registers)
 #endif
@@ -218,8 +226,11 @@ __device__ __forceinline__ float ks_enter_down_w(float Q, float G, float carry) 
 // ================================================================================================
 // Forward
 // ================================================================================================
+#ifndef NZ_FWD_MINB
+#define NZ_FWD_MINB 2  // resident CTAs per SM the forward is compiled for (register cap 65536 / (256 * MINB))
+#endif
 template <typename T, int M, int LPR, int WARPS, int NQ, bool kTMA, bool kHasZ>
-__global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
+__global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LPR > 128) ? 1 : NZ_FWD_MINB)
     scan_fwd_kernel(const __grid_constant__ ScanKArgs a) {
   using Cfg = ScanCfg<T, M, LPR, WARPS, kHasZ, false>;
   constexpr int R = Cfg::R, TL = Cfg::TL, ROWB = Cfg::ROWB, SEGB = Cfg::SEGB, RPW = Cfg::RPW;
@@ -243,7 +254,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sl = lane / RPW;                      // segment (time) index inside the row
   const int rloc = warp * RPW + lane % RPW;       // row inside the CTA
-  const int N = a.dstate;
+  const int N = kTMA ? kMaxState : a.dstate;  // the TMA path only runs d_state == 16
   const uint32_t segoff = sl * SEGB;
   const LanePre<M, T> lp(segoff);
   const int NP = (N + NQ - 1) / NQ * NQ;  // states are processed NQ at a time; rows >= N of the tiles are zero
@@ -399,7 +410,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     }
 
     if (a.trace && tid == 0) tr_loop = gtime_ns();
-#pragma unroll 1
+    NZ_UNROLL(NZ_FWD_UNROLL)
     for (int n = 0; n < NP; n += NQ) {  // NQ independent states per trip (instruction-level parallelism)
       float hc[NQ], P[NQ], H[NQ];
       unsigned ctag[NQ];
@@ -553,7 +564,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   const int sl = lane / RPW;
   const int rw = lane % RPW;
   const int rloc = warp * RPW + rw;
-  const int N = a.dstate;
+  const int N = a.dstate;  // (a compile-time 16 on the TMA path measured 6% slower: register allocation)
   const uint32_t segoff = sl * SEGB;
   const LanePre<M, T> lp(segoff);
   // slab addressing (loop invariant): row = rloc, the lane's M floats.  Odd rows flip 16-byte-chunk
@@ -788,7 +799,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     }
     float* gsp = sm_gs + rloc * (LPR / 2) + (sl >> 1);
 
-#pragma unroll 1
+    NZ_UNROLL(NZ_BWD_UNROLL)
     for (int n = 0; n < N; ++n, ++g) {
       const float A2 = sm_A2[rloc * kMaxState + n];
       const float An = A2 * kLn2;

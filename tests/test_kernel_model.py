@@ -1,19 +1,21 @@
 """CPU model of the CUDA kernels' decomposition (no GPU needed).
 
-nnuzoo_b200/csrc/scan_kernels.cuh splits every row into chunks of NZ_CHUNK steps, every chunk into
-LPR lane segments of M steps, folds a segment sequentially, combines the lane aggregates with a
-Kogge-Stone scan, carries state across chunks, and (backward) walks the chunks last-to-first using
-the forward's end-of-chunk checkpoints.  This file restates exactly that dataflow in numpy -- same
-identities, same carries, same masking of the ragged tail -- and checks it against the oracle, so
-an algebra mistake is caught here rather than on the GPU.
+nnuzoo_b200/csrc/scan_kernels.cuh splits every row into tiles (forward: 16 lane segments x 16 steps
+= 256 steps, backward: 16 x 8 = 128 steps), folds a segment sequentially, combines the lane
+aggregates with a Kogge-Stone scan, hands the state from tile to tile along L (the chained {value,
+tag} slots), writes a checkpoint of h every NZ_CHUNK = 128 steps (two per forward tile) and
+(backward) walks the tiles last-to-first restarting from those checkpoints.  This file restates
+exactly that dataflow in numpy -- same identities, same carries, same masking of the ragged tail --
+and checks it against the oracle, so an algebra mistake is caught here rather than on the GPU.
 """
 import numpy as np
 import pytest
 
 from oracle import scan_oracle
 
-M, LPR = 8, 32
-TL = M * LPR
+CK = 128                 # NZ_CHUNK: checkpoint interval
+MF, LF = 16, 16          # forward: steps per lane, lane segments per row  (scan_inst.cuh NZ_FWD_M / NZ_FWD_LPR)
+MB, LB = 8, 16           # backward                                      (NZ_BWD_M / NZ_BWD_LPR)
 
 
 def _softplus(x):
@@ -23,6 +25,7 @@ def _softplus(x):
 def _ks_inclusive(P, H):
     """Kogge-Stone inclusive scan of (P, H) pairs over the lane axis, op = later o earlier."""
     P, H = P.copy(), H.copy()
+    LPR = P.shape[0]
     off = 1
     while off < LPR:
         Pp = np.concatenate([np.ones(off), P[:-off]])
@@ -36,6 +39,7 @@ def _ks_inclusive(P, H):
 
 def _ks_suffix(Q, G):
     Q, G = Q.copy(), G.copy()
+    LPR = Q.shape[0]
     off = 1
     while off < LPR:
         Qn = np.concatenate([Q[off:], np.ones(off)])
@@ -50,10 +54,13 @@ def _ks_suffix(Q, G):
 def model_row(u, delta, A, B, C, D, z, bias, softplus, dout):
     """One (batch, dim) row through the kernels' dataflow.  B, C: (N, L)."""
     L, N = u.shape[0], A.shape[0]
-    nch = (L + TL - 1) // TL
-    pad = nch * TL - L
+    TLF, TLB = MF * LF, MB * LB
+    assert TLB == CK and TLF % CK == 0
+    nchf = (L + TLF - 1) // TLF
+    nck = (L + CK - 1) // CK
+    pad = nchf * TLF - L  # the forward padding covers the backward's (TLB divides TLF)
     padv = lambda a: np.concatenate([a, np.zeros(pad)])  # noqa: E731  (TMA zero-fills the tail)
-    valid = np.arange(nch * TL) < L
+    valid = np.arange(nchf * TLF) < L
     uu, dr, go = padv(u), padv(delta), padv(dout)
     zz = padv(z) if z is not None else None
     Bp = np.concatenate([B, np.zeros((N, pad))], axis=1)
@@ -62,10 +69,11 @@ def model_row(u, delta, A, B, C, D, z, bias, softplus, dout):
     dl = np.where(valid, _softplus(x) if softplus else x, 0.0)
     dlu = dl * uu
     # ------------------------------ forward ------------------------------
+    M, LPR, TL = MF, LF, TLF
     y = D * uu
-    ckpt = np.zeros((nch, N))
-    hc = np.zeros(N)
-    for c in range(nch):
+    ckpt = np.zeros((nck, N))
+    hc = np.zeros(N)  # the chained hand-off: h at the end of the previous tile
+    for c in range(nchf):
         sl = slice(c * TL, (c + 1) * TL)
         for n in range(N):
             a = np.exp(dl[sl] * A[n]).reshape(LPR, M)
@@ -78,15 +86,19 @@ def model_row(u, delta, A, B, C, D, z, bias, softplus, dout):
             Pex = np.concatenate([[1.0], Pi[:-1]])
             Hex = np.concatenate([[0.0], Hi[:-1]])
             h = Pex * hc[n] + Hex
-            hnew = Pi[-1] * hc[n] + Hi[-1]
+            hend = Pi * hc[n] + Hi  # state at the end of every lane segment
+            for seg in range(LPR):  # lanes whose segment ends a checkpoint interval write it
+                if (seg + 1) % (CK // M) == 0:
+                    ck = c * (TL // CK) + (seg + 1) // (CK // M) - 1
+                    if ck < nck:
+                        ckpt[ck, n] = hend[seg]
             cv = Cp[n, sl].reshape(LPR, M)
             yy = y[sl].reshape(LPR, M)
             for i in range(M):
                 h = a[:, i] * h + b[:, i]
                 yy[:, i] += cv[:, i] * h
             y[sl] = yy.reshape(-1)
-            hc[n] = hnew
-            ckpt[c, n] = hnew
+            hc[n] = hend[-1]
     out = y.copy()
     if zz is not None:
         out = out * zz / (1 + np.exp(-zz))
@@ -97,14 +109,17 @@ def model_row(u, delta, A, B, C, D, z, bias, softplus, dout):
         sg = 1 / (1 + np.exp(-zz))
         dzf = dy * sg * (1 + zz * (1 - sg))
         dy = dy * zz * sg
-    du = np.zeros(nch * TL)
-    dd = np.zeros(nch * TL)
+    M, LPR, TL = MB, LB, TLB
+    nch = nck  # one backward tile per checkpoint interval
+    tot = nchf * TLF
+    du = np.zeros(tot)
+    dd = np.zeros(tot)
     dA = np.zeros(N)
-    dB = np.zeros((N, nch * TL))
-    dC = np.zeros((N, nch * TL))
+    dB = np.zeros((N, tot))
+    dC = np.zeros((N, tot))
     yv = D * uu
-    dhc = np.zeros(N)
-    anx = np.zeros(N)
+    dhc = np.zeros(N)  # the chained hand-off: dh leaving the later tile
+    anx = np.zeros(N)  # a of the later tile's first step (the kernel recomputes it from delta)
     for c in range(nch - 1, -1, -1):
         sl = slice(c * TL, (c + 1) * TL)
         sB = np.zeros((LPR, M))

@@ -1,0 +1,62 @@
+"""Summarise an `ncu --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum`
+launch list of `bench.py --steps 1`:
+
+  * per-kernel share of the summed launch time (compare with bench.py's CUDA-event share; ncu's
+    absolute times are cold-cache and serialised),
+  * average DRAM traffic per scan_bwd launch next to the average algorithmic bytes per launch
+    -> profiles/r01_bwd_traffic.json, which bench.py reports as roofline.traffic.
+
+    python tools/ncu_traffic.py gpurun_out/launches_r01.csv [profiles/r01_bwd_traffic.json]
+"""
+import collections
+import csv
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+
+def main(path, out=None):
+    rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
+    hdr = rows[0]
+    ik, im, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    iid = hdr.index("ID")
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        d = per.setdefault(r[iid], {"kernel": r[ik]})
+        v = float(r[iv].replace(",", ""))
+        unit = r[iu]
+        if r[im].startswith("gpu__time_duration"):
+            v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)  # -> us
+        else:
+            v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)  # -> bytes
+        d[r[im]] = v
+    tot = sum(d.get("gpu__time_duration.sum", 0.0) for d in per.values())
+    by = collections.Counter()
+    cnt = collections.Counter()
+    for d in per.values():
+        name = d["kernel"].split("<")[0].split("(")[0]
+        by[name] += d.get("gpu__time_duration.sum", 0.0)
+        cnt[name] += 1
+    print(f"{len(per)} launches, {tot / 1e3:.2f} ms summed (serialised, cold cache)")
+    for k, v in by.most_common():
+        print(f"  {k:40s} launches {cnt[k]:4d}  time {v / 1e3:9.3f} ms  share {v / tot:6.1%}")
+    bwd = [d for d in per.values() if "scan_bwd" in d["kernel"]]
+    if bwd and "dram__bytes_read.sum" in bwd[0]:
+        traffic = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in bwd) / len(bwd)
+        scans = bench.m2net_scan_list(512)
+        algo = sum(bench.scan_bytes(bench.BATCH, kd, L)["bwd"] for kd, L in scans) / len(scans)
+        print(f"scan_bwd: {len(bwd)} launches, DRAM traffic {traffic / 1e6:.1f} MB per launch vs algorithmic "
+              f"{algo / 1e6:.1f} MB per launch (x{traffic / algo:.3f})")
+        if out:
+            json.dump({"dram_bytes_per_launch": traffic, "algorithmic_bytes_per_launch": algo, "launches": len(bwd),
+                       "ratio": traffic / algo, "source": os.path.basename(path),
+                       "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+                              "--clock-control none, bench.py --steps 1 (NZ_BENCH_PROFILE=1)"}, open(out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None)
