@@ -290,7 +290,11 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
       pool_dev = dev;
     }
   }
-  NzScanDesc d = *h;
+  // Pipeline over batch slices on three streams: H2D of slice i+1 overlaps the kernels of slice i and the
+  // D2H of slice i-1 (PCIe is full duplex; the staged copies, not the kernels, bound this entry point).
+  static thread_local cudaStream_t s_in = nullptr, s_out = nullptr;
+  static thread_local cudaEvent_t ev_in[64], ev_cmp[64], ev_start = nullptr, ev_done = nullptr;
+  static thread_local bool ev_ready = false;
   char* pool = nullptr;
   size_t off = 0;
   auto carve = [&](size_t bytes) {
@@ -298,11 +302,23 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
     off += (bytes + 255) & ~(size_t)255;
     return p;
   };
-  const size_t total = 8 * (row_bytes + 256) + 2 * (bc_bytes + 256) + 2 * (bc_f32 + 256) +
-                       (size_t)Bt * Dm * nch * N * 4 + 6 * ((size_t)Dm * N * 4 + 256) + 4096 +
-                       (size_t)nz_scan_workspace_bytes(h) + 256;
-  NZ_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pool), total, st));
+  if (!ev_ready) {
+    NZ_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    NZ_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 64; ++i) {
+      NZ_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+      NZ_CUDA(cudaEventCreateWithFlags(&ev_cmp[i], cudaEventDisableTiming));
+    }
+    NZ_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    NZ_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+    ev_ready = true;
+  }
   {
+    const int nsl = (int)(Bt < 64 ? Bt : 64);  // one slice per batch entry (at most 64 slices)
+    const size_t total = 8 * (row_bytes + 256) + 2 * (bc_bytes + 256) + 2 * (bc_f32 + 256) +
+                         (size_t)Bt * Dm * nch * N * 4 + 6 * ((size_t)Dm * N * 4 + 256) + 4096 +
+                         (size_t)nz_scan_workspace_bytes(h) + 256;
+    NZ_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pool), total, st));
     char* du_ = carve(row_bytes); char* dd_ = carve(row_bytes); char* dz_ = carve(row_bytes);
     char* u_ = carve(row_bytes); char* dl_ = carve(row_bytes); char* z_ = carve(row_bytes);
     char* out_ = carve(row_bytes); char* go_ = carve(row_bytes);
@@ -312,53 +328,88 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
     char* A_ = carve((size_t)Dm * N * 4); char* dA_ = carve((size_t)Dm * N * 4);
     char* D_ = carve((size_t)Dm * 4); char* bias_ = carve((size_t)Dm * 4);
     char* dD_ = carve((size_t)Dm * 4); char* db_ = carve((size_t)Dm * 4);
-    d.workspace = carve((size_t)nz_scan_workspace_bytes(h));
-    d.workspace_bytes = nz_scan_workspace_bytes(h);
-    NZ_CUDA(cudaMemcpyAsync(u_, h->u, row_bytes, cudaMemcpyHostToDevice, st));
-    NZ_CUDA(cudaMemcpyAsync(dl_, h->delta, row_bytes, cudaMemcpyHostToDevice, st));
-    NZ_CUDA(cudaMemcpyAsync(B_, h->B, bc_bytes, cudaMemcpyHostToDevice, st));
-    NZ_CUDA(cudaMemcpyAsync(C_, h->C, bc_bytes, cudaMemcpyHostToDevice, st));
-    NZ_CUDA(cudaMemcpyAsync(A_, h->A, (size_t)Dm * N * 4, cudaMemcpyHostToDevice, st));
-    d.u = u_; d.delta = dl_; d.B = B_; d.C = C_; d.A = reinterpret_cast<float*>(A_); d.A_stride = N;
-    d.out = out_; d.x = reinterpret_cast<float*>(x_);
-    if (h->D) { NZ_CUDA(cudaMemcpyAsync(D_, h->D, (size_t)Dm * 4, cudaMemcpyHostToDevice, st)); d.D = reinterpret_cast<float*>(D_); }
-    if (h->delta_bias) {
-      NZ_CUDA(cudaMemcpyAsync(bias_, h->delta_bias, (size_t)Dm * 4, cudaMemcpyHostToDevice, st));
-      d.delta_bias = reinterpret_cast<float*>(bias_);
-    }
-    if (h->z) {
-      NZ_CUDA(cudaMemcpyAsync(z_, h->z, row_bytes, cudaMemcpyHostToDevice, st));
-      d.z = z_; d.z_stride[0] = Dm * L; d.z_stride[1] = L;
-    }
-    rc = nz_scan_fwd(&d, stream);
-    if (rc) goto done;
-    NZ_CUDA(cudaMemcpyAsync(h->out, out_, row_bytes, cudaMemcpyDeviceToHost, st));
-    if (h->x) NZ_CUDA(cudaMemcpyAsync(h->x, x_, (size_t)Bt * Dm * nch * N * 4, cudaMemcpyDeviceToHost, st));
+    char* ws_ = carve((size_t)nz_scan_workspace_bytes(h));
+    // the side streams start after the allocation (and whatever precedes this call on `stream`)
+    NZ_CUDA(cudaEventRecord(ev_start, st));
+    NZ_CUDA(cudaStreamWaitEvent(s_in, ev_start, 0));
+    NZ_CUDA(cudaStreamWaitEvent(s_out, ev_start, 0));
+    // parameters + zeroed accumulators first
+    NZ_CUDA(cudaMemcpyAsync(A_, h->A, (size_t)Dm * N * 4, cudaMemcpyHostToDevice, s_in));
+    if (h->D) NZ_CUDA(cudaMemcpyAsync(D_, h->D, (size_t)Dm * 4, cudaMemcpyHostToDevice, s_in));
+    if (h->delta_bias) NZ_CUDA(cudaMemcpyAsync(bias_, h->delta_bias, (size_t)Dm * 4, cudaMemcpyHostToDevice, s_in));
     if (bwd) {
-      NZ_CUDA(cudaMemcpyAsync(go_, h->dout, row_bytes, cudaMemcpyHostToDevice, st));
-      d.dout = go_; d.dout_stride[0] = Dm * L; d.dout_stride[1] = L;
-      d.du = du_; d.ddelta = dd_; d.dz = h->z ? dz_ : nullptr;
-      d.dA = reinterpret_cast<float*>(dA_); d.dB = reinterpret_cast<float*>(dB_); d.dC = reinterpret_cast<float*>(dC_);
-      d.dD = h->dD ? reinterpret_cast<float*>(dD_) : nullptr;
-      d.ddelta_bias = h->ddelta_bias ? reinterpret_cast<float*>(db_) : nullptr;
-      NZ_CUDA(cudaMemsetAsync(dA_, 0, (size_t)Dm * N * 4, st));
-      NZ_CUDA(cudaMemsetAsync(dB_, 0, bc_f32, st));
-      NZ_CUDA(cudaMemsetAsync(dC_, 0, bc_f32, st));
-      NZ_CUDA(cudaMemsetAsync(dD_, 0, (size_t)Dm * 4, st));
-      NZ_CUDA(cudaMemsetAsync(db_, 0, (size_t)Dm * 4, st));
-      rc = nz_scan_bwd(&d, stream);
-      if (rc) goto done;
-      NZ_CUDA(cudaMemcpyAsync(h->du, du_, row_bytes, cudaMemcpyDeviceToHost, st));
-      NZ_CUDA(cudaMemcpyAsync(h->ddelta, dd_, row_bytes, cudaMemcpyDeviceToHost, st));
-      if (h->z) NZ_CUDA(cudaMemcpyAsync(h->dz, dz_, row_bytes, cudaMemcpyDeviceToHost, st));
-      NZ_CUDA(cudaMemcpyAsync(h->dA, dA_, (size_t)Dm * N * 4, cudaMemcpyDeviceToHost, st));
-      NZ_CUDA(cudaMemcpyAsync(h->dB, dB_, bc_f32, cudaMemcpyDeviceToHost, st));
-      NZ_CUDA(cudaMemcpyAsync(h->dC, dC_, bc_f32, cudaMemcpyDeviceToHost, st));
-      if (h->dD) NZ_CUDA(cudaMemcpyAsync(h->dD, dD_, (size_t)Dm * 4, cudaMemcpyDeviceToHost, st));
-      if (h->ddelta_bias) NZ_CUDA(cudaMemcpyAsync(h->ddelta_bias, db_, (size_t)Dm * 4, cudaMemcpyDeviceToHost, st));
+      NZ_CUDA(cudaMemsetAsync(dA_, 0, (size_t)Dm * N * 4, s_in));
+      NZ_CUDA(cudaMemsetAsync(dB_, 0, bc_f32, s_in));
+      NZ_CUDA(cudaMemsetAsync(dC_, 0, bc_f32, s_in));
+      NZ_CUDA(cudaMemsetAsync(dD_, 0, (size_t)Dm * 4, s_in));
+      NZ_CUDA(cudaMemsetAsync(db_, 0, (size_t)Dm * 4, s_in));
     }
+    for (int i = 0; i < nsl; ++i) {
+      const int64_t b0 = Bt * i / nsl, b1 = Bt * (i + 1) / nsl, nb = b1 - b0;
+      const size_t ro = (size_t)b0 * Dm * L * es, rb = (size_t)nb * Dm * L * es;
+      const size_t bo = (size_t)b0 * G * N * L * es, bb = (size_t)nb * G * N * L * es;
+      const size_t fo = (size_t)b0 * G * N * L * 4, fb = (size_t)nb * G * N * L * 4;
+      const size_t xo = (size_t)b0 * Dm * nch * N * 4, xb = (size_t)nb * Dm * nch * N * 4;
+      auto hp = [](const void* p, size_t o) { return static_cast<const char*>(p) + o; };
+      auto hq = [](void* p, size_t o) { return static_cast<char*>(p) + o; };
+      // ---- host -> device ----
+      NZ_CUDA(cudaMemcpyAsync(u_ + ro, hp(h->u, ro), rb, cudaMemcpyHostToDevice, s_in));
+      NZ_CUDA(cudaMemcpyAsync(dl_ + ro, hp(h->delta, ro), rb, cudaMemcpyHostToDevice, s_in));
+      NZ_CUDA(cudaMemcpyAsync(B_ + bo, hp(h->B, bo), bb, cudaMemcpyHostToDevice, s_in));
+      NZ_CUDA(cudaMemcpyAsync(C_ + bo, hp(h->C, bo), bb, cudaMemcpyHostToDevice, s_in));
+      if (h->z) NZ_CUDA(cudaMemcpyAsync(z_ + ro, hp(h->z, ro), rb, cudaMemcpyHostToDevice, s_in));
+      if (bwd) NZ_CUDA(cudaMemcpyAsync(go_ + ro, hp(h->dout, ro), rb, cudaMemcpyHostToDevice, s_in));
+      NZ_CUDA(cudaEventRecord(ev_in[i], s_in));
+      // ---- kernels on the caller's stream ----
+      NZ_CUDA(cudaStreamWaitEvent(st, ev_in[i], 0));
+      NzScanDesc d = *h;
+      d.batch = (int32_t)nb;
+      d.u = u_ + ro; d.delta = dl_ + ro; d.B = B_ + bo; d.C = C_ + bo;
+      d.A = reinterpret_cast<float*>(A_); d.A_stride = N;
+      d.D = h->D ? reinterpret_cast<float*>(D_) : nullptr;
+      d.delta_bias = h->delta_bias ? reinterpret_cast<float*>(bias_) : nullptr;
+      d.z = h->z ? z_ + ro : nullptr; d.z_stride[0] = Dm * L; d.z_stride[1] = L;
+      d.out = out_ + ro; d.x = reinterpret_cast<float*>(x_ + xo);
+      d.workspace = ws_; d.workspace_bytes = nz_scan_workspace_bytes(h);
+      rc = nz_scan_fwd(&d, stream);
+      if (rc) goto done;
+      if (bwd) {
+        d.dout = go_ + ro; d.dout_stride[0] = Dm * L; d.dout_stride[1] = L;
+        d.du = du_ + ro; d.ddelta = dd_ + ro; d.dz = h->z ? dz_ + ro : nullptr;
+        d.dA = reinterpret_cast<float*>(dA_);
+        d.dB = reinterpret_cast<float*>(dB_ + fo); d.dC = reinterpret_cast<float*>(dC_ + fo);
+        d.dD = h->dD ? reinterpret_cast<float*>(dD_) : nullptr;
+        d.ddelta_bias = h->ddelta_bias ? reinterpret_cast<float*>(db_) : nullptr;
+        rc = nz_scan_bwd(&d, stream);
+        if (rc) goto done;
+      }
+      NZ_CUDA(cudaEventRecord(ev_cmp[i], st));
+      // ---- device -> host ----
+      NZ_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[i], 0));
+      NZ_CUDA(cudaMemcpyAsync(hq(h->out, ro), out_ + ro, rb, cudaMemcpyDeviceToHost, s_out));
+      if (h->x) NZ_CUDA(cudaMemcpyAsync(hq(h->x, xo), x_ + xo, xb, cudaMemcpyDeviceToHost, s_out));
+      if (bwd) {
+        NZ_CUDA(cudaMemcpyAsync(hq(h->du, ro), du_ + ro, rb, cudaMemcpyDeviceToHost, s_out));
+        NZ_CUDA(cudaMemcpyAsync(hq(h->ddelta, ro), dd_ + ro, rb, cudaMemcpyDeviceToHost, s_out));
+        if (h->z) NZ_CUDA(cudaMemcpyAsync(hq(h->dz, ro), dz_ + ro, rb, cudaMemcpyDeviceToHost, s_out));
+        NZ_CUDA(cudaMemcpyAsync(hq(h->dB, fo), dB_ + fo, fb, cudaMemcpyDeviceToHost, s_out));
+        NZ_CUDA(cudaMemcpyAsync(hq(h->dC, fo), dC_ + fo, fb, cudaMemcpyDeviceToHost, s_out));
+      }
+    }
+    if (bwd) {  // the (dim)-shaped sums are complete after the last slice
+      NZ_CUDA(cudaMemcpyAsync(h->dA, dA_, (size_t)Dm * N * 4, cudaMemcpyDeviceToHost, s_out));
+      if (h->dD) NZ_CUDA(cudaMemcpyAsync(h->dD, dD_, (size_t)Dm * 4, cudaMemcpyDeviceToHost, s_out));
+      if (h->ddelta_bias) NZ_CUDA(cudaMemcpyAsync(h->ddelta_bias, db_, (size_t)Dm * 4, cudaMemcpyDeviceToHost, s_out));
+    }
+    // join the side streams back into the caller's stream
+    NZ_CUDA(cudaEventRecord(ev_done, s_out));
+    NZ_CUDA(cudaStreamWaitEvent(st, ev_done, 0));
   }
 done:
+  if (ev_ready) {  // nothing of this call may still be in flight when the pool memory is released
+    cudaStreamSynchronize(s_in);
+    cudaStreamSynchronize(s_out);
+  }
   if (pool) cudaFreeAsync(pool, st);
   {
     cudaError_t e2 = cudaStreamSynchronize(st);

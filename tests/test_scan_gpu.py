@@ -159,6 +159,9 @@ SHAPES = [
     (2, 6, 2, 16, 320, False),      # 3 rows per group -> one-row-per-CTA kernel
     (1, 8, 1, 8, 512, False),       # d_state 8
     (1, 8, 1, 16, 1, False),        # L = 1
+    (2, 64, 4, 16, 512, False),     # exactly one 16-row tile per group: TMA path, plain dB/dC stores
+    (1, 96, 2, 16, 384, True),      # 48 rows per group: three row blocks share dB/dC (vector atomics), z gate
+    (3, 40, 2, 16, 640, False),     # 20 rows per group: generic path with a partly filled second row block
 ]
 
 
@@ -242,3 +245,41 @@ def test_rejects_what_it_does_not_implement():
                           torch.zeros(1, 1, 32, 16, device=dev))
     with pytest.raises(RuntimeError):
         selective_scan_fn(u.cpu(), u.cpu(), torch.zeros(8, 16), torch.zeros(1, 1, 16, 16), torch.zeros(1, 1, 16, 16))
+
+
+def test_host_entry_point_matches_device_path():
+    """nz_scan_fwd_bwd_host (host pointers, pipelined over batch slices) == the device-pointer path."""
+    import ctypes
+
+    from nnuzoo_b200 import _native
+    lib = _native.lib()
+    _native.bind_device(0)
+    batch, dim, G, N, L = 3, 64, 2, 16, 768
+    inp, gout = _seeded(batch, dim, G, N, L, True, seed=7)
+    dev_inp = {k: (None if v is None else v.to(_dev()).requires_grad_(True)) for k, v in inp.items()}
+    out, last, grads = _run(dev_inp, True, gout.to(_dev()))
+    f = lambda a: np.ascontiguousarray(a.detach().cpu().numpy() if hasattr(a, "detach") else a, dtype=np.float32)  # noqa: E731
+    h = {k: f(v) for k, v in inp.items() if v is not None}
+    res = {k: np.empty_like(h["u"]) for k in ("out", "du", "ddelta", "dz")}
+    res.update(dB=np.empty_like(h["B"]), dC=np.empty_like(h["C"]), dA=np.empty_like(h["A"]),
+               dD=np.empty_like(h["D"]), db=np.empty_like(h["delta_bias"]))
+    hg = f(gout)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)  # noqa: E731
+    d = _native.NzScanDesc()
+    d.batch, d.dim, d.dstate, d.ngroups, d.seqlen = batch, dim, N, G, L
+    d.dtype, d.delta_softplus = 0, 1
+    d.u, d.delta, d.A, d.B, d.C, d.D, d.z, d.delta_bias = (p(h[k]) for k in ("u", "delta", "A", "B", "C", "D", "z", "delta_bias"))
+    for st in (d.u_stride, d.delta_stride, d.z_stride, d.out_stride, d.dout_stride):
+        st[0], st[1] = dim * L, L
+    for st in (d.B_stride, d.C_stride):
+        st[0], st[1], st[2] = G * N * L, N * L, L
+    d.A_stride = N
+    d.out, d.dout = p(res["out"]), p(hg)
+    d.du, d.ddelta, d.dz = p(res["du"]), p(res["ddelta"]), p(res["dz"])
+    d.dA, d.dB, d.dC, d.dD, d.ddelta_bias = p(res["dA"]), p(res["dB"]), p(res["dC"]), p(res["dD"]), p(res["db"])
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _native.check(lib.nz_scan_fwd_bwd_host(ctypes.byref(d), stream), "nz_scan_fwd_bwd_host")
+    pairs = {"out": out, "du": grads["du"], "ddelta": grads["ddelta"], "dz": grads["dz"], "dB": grads["dB"],
+             "dC": grads["dC"], "dA": grads["dA"], "dD": grads["dD"], "db": grads["ddelta_bias"]}
+    for k, ref in pairs.items():
+        assert rel_err(res[k], ref.detach().float().cpu().numpy()) < 1e-5, k
