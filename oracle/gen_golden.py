@@ -14,6 +14,7 @@ What is recorded (all seeds fixed, sizes tiny so the fixtures stay small):
   module_*.npz: state_dict + input + output + input/parameter gradients of reference
                 SS2D (m2net.py:39-225) and SSND 2-D / 3-D (ssnd2net.py:73-318) modules, with the
                 reference's selective_scan_ref as the scan.
+  module_mamba_*.npz: the vendored Mamba block (seg_mamba/mamba_simple.py:37-357), bimamba none / v2 / v3.
   MANIFEST.json: case list plus the agreement of oracle/torch_port.py and oracle/scan_oracle.c with
                 the verbatim reference at generation time.
 """
@@ -204,6 +205,37 @@ def gen_module(manifest):
         manifest["module"][name] = dict(x_shape=list(xshape), y_abs_mean=float(y.abs().mean()))
 
 
+def gen_mamba(manifest):
+    """module_mamba_*.npz: the reference's vendored Mamba block (mamba_simple.py:37-357), uni-, bi- (v2) and
+    tri-directional (v3), fast path (fused call replaced by its op-for-op CPU stand-in, ref_loader.mamba_simple)
+    and, for "none", also the reference's own slow path -- the two must agree."""
+    ms = ref_loader.mamba_simple()
+    specs = {"module_mamba_none": ("none", (2, 24, 16)), "module_mamba_v2": ("v2", (2, 20, 16)),
+             "module_mamba_v3": ("v3", (1, 30, 32))}
+    for i, (name, (kind, xshape)) in enumerate(specs.items()):
+        torch.manual_seed(300 + i)
+        mod = ms.Mamba(d_model=xshape[-1], bimamba_type=kind, nslices=5).eval()
+        with torch.no_grad():  # move the scan parameters off their symmetric init
+            for p in (mod.A_log, mod.A_b_log, mod.A_s_log, mod.D, mod.D_b, mod.D_s):
+                p.add_(0.1 * torch.randn_like(p))
+        x = torch.randn(*xshape, requires_grad=True)
+        y = mod(x)
+        if kind == "none":
+            mod.use_fast_path = False
+            y_slow = mod(x)
+            mod.use_fast_path = True
+            assert float((y - y_slow).abs().max()) < 1e-5 * float(y.abs().max() + 1e-9)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        rec = {"x": _np(x), "y": _np(y), "gy": _np(gy), "gx": _np(x.grad)}
+        for k, v in mod.state_dict().items():
+            rec["sd_" + k] = _np(v)
+        for k, p in mod.named_parameters():
+            rec["gp_" + k] = _np(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+        manifest["module"][name] = dict(x_shape=list(xshape), y_abs_mean=float(y.abs().mean()), bimamba_type=kind)
+
+
 def main():
     assert ref_loader.available(), "run in the build container: /root/reference is required"
     os.makedirs(GOLD, exist_ok=True)
@@ -214,6 +246,7 @@ def main():
     gen_scan(manifest)
     gen_cross(manifest)
     gen_module(manifest)
+    gen_mamba(manifest)
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print(json.dumps(manifest, indent=1, sort_keys=True))

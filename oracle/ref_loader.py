@@ -170,6 +170,50 @@ def selective_scan_ref():
                      "nnunetv2/nets/seg_mamba/selective_scan_interface.py").selective_scan_ref
 
 
+def mamba_simple():
+    """The reference's vendored Mamba block (seg_mamba/mamba_simple.py) wired to run on the CPU:
+    ``selective_scan_fn`` := the reference's own selective_scan_ref, ``causal_conv1d_fn`` := None (the
+    file's own F.conv1d fallback, :316-317), and the CUDA-only fused ``mamba_inner_fn*`` replaced by a
+    stand-in that follows MambaInnerFnNoOutProj.forward (selective_scan_interface.py:159-226) op for op
+    with those two substitutions."""
+    import torch.nn.functional as F
+    from einops import rearrange
+
+    ref = selective_scan_ref()
+    # mamba_simple.py:13-16 needs both names importable (its except branch cannot run: `a, b = None`)
+    cc = sys.modules.get("causal_conv1d") or types.ModuleType("causal_conv1d")
+    cc.causal_conv1d_fn = None
+    cc.causal_conv1d_update = None
+    sys.modules["causal_conv1d"] = cc
+    mod = load_file("ref_mamba_simple", "nnunetv2/nets/seg_mamba/mamba_simple.py")
+    mod.selective_scan_fn = ref
+    mod.causal_conv1d_fn = None
+
+    def inner_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None,
+                          D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+        L = xz.shape[-1]
+        delta_rank = delta_proj_weight.shape[1]
+        d_state = A.shape[-1]
+        x, z = xz.chunk(2, dim=1)
+        w = conv1d_weight.shape[-1]
+        x = F.silu(F.conv1d(x, conv1d_weight, conv1d_bias, padding=w - 1, groups=x.shape[1])[..., :L])
+        x_dbl = F.linear(rearrange(x, "b d l -> (b l) d"), x_proj_weight)
+        delta = rearrange(delta_proj_weight @ x_dbl[:, :delta_rank].t(), "d (b l) -> b d l", l=L)
+        Bv = rearrange(x_dbl[:, delta_rank:delta_rank + d_state], "(b l) dstate -> b 1 dstate l", l=L).contiguous()
+        Cv = rearrange(x_dbl[:, -d_state:], "(b l) dstate -> b 1 dstate l", l=L).contiguous()
+        return ref(x, delta, A, Bv, Cv, D, z=z, delta_bias=delta_bias, delta_softplus=delta_softplus)
+
+    def inner(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias, A,
+              B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+        y = inner_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
+                              delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+        return F.linear(rearrange(y, "b d l -> b l d"), out_proj_weight, out_proj_bias)
+
+    mod.mamba_inner_fn_no_out_proj = inner_no_out_proj
+    mod.mamba_inner_fn = inner
+    return mod
+
+
 def m2net():
     return load_file("ref_m2net", "nnunetv2/nets/m2net.py")
 

@@ -95,3 +95,23 @@ def test_modules_keep_the_reference_state_dict_contract():
     assert "convnd.conv.weight" in s.state_dict() and tuple(s.state_dict()["convnd.conv.weight"].shape) == (32, 1, 3, 3, 3)
     with pytest.raises(Exception):
         SSND(2, "other", d_model=8)
+
+
+def test_mamba_block_loads_the_reference_state_dict():
+    """seg_mamba/mamba_simple.py:37-189: same parameter names / shapes, incl. the *_b and *_s sets the
+    reference creates unconditionally (checked against a state_dict recorded from the reference)."""
+    import numpy as np
+
+    from nnuzoo_b200 import Mamba
+    rec = np.load(os.path.join(ROOT, "tests", "golden", "module_mamba_v3.npz"))
+    sd = {k[3:]: torch.from_numpy(rec[k]) for k in rec.files if k.startswith("sd_")}
+    m = Mamba(d_model=32, bimamba_type="v3", nslices=5)
+    m.load_state_dict(sd, strict=True)
+    assert m.dt_rank == 2 and m.d_inner == 64
+    assert m.A_log._no_weight_decay and m.D_s._no_weight_decay and m.dt_proj.bias._no_reinit
+    fresh = Mamba(d_model=32)
+    assert torch.allclose(fresh.A_b_log[0].exp(), torch.arange(1, 17).float())
+    sp = torch.nn.functional.softplus(fresh.dt_proj.bias)
+    assert float(sp.min()) >= 1e-4 - 1e-9 and float(sp.max()) <= 0.1 + 1e-6
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 10, 32))

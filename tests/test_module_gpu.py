@@ -1,7 +1,8 @@
 """Module-level parity: our SS2D / SSND against the reference modules' recorded behaviour.
 
 tests/golden/module_*.npz hold state_dict + input + output + gradients of the REFERENCE modules
-(m2net.py:39-225, ssnd2net.py:73-318) run with the reference's own selective_scan_ref.  The GEMMs
+(m2net.py:39-225, ssnd2net.py:73-318, seg_mamba/mamba_simple.py:37-357) run with the reference's own
+selective_scan_ref.  The GEMMs
 around the scan run in a different order on the GPU, so the tolerance is the scan's (rel 1e-3).
 """
 import numpy as np
@@ -14,9 +15,11 @@ pytestmark = pytest.mark.gpu
 
 
 def _build(name, rec):
-    from nnuzoo_b200 import SS2D, SSND
+    from nnuzoo_b200 import SS2D, SSND, Mamba
     d_model = rec["x"].shape[-1]
-    if name.startswith("module_ss2d"):
+    if name.startswith("module_mamba"):
+        mod = Mamba(d_model=d_model, bimamba_type=name.rsplit("_", 1)[1], nslices=5)
+    elif name.startswith("module_ss2d"):
         mod = SS2D(d_model=d_model)
     elif "ssnd2d" in name:
         mod = SSND(spatial_dims=2, factorization_type="cross-scan", d_model=d_model)
