@@ -325,7 +325,6 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
       }
     }
     const unsigned long long* cin = a.carry + (rowg * 2 + ((c - 1) & 1)) * kMaxState;
-    unsigned long long* cout = a.carry + (rowg * 2 + (c & 1)) * kMaxState;
     const bool chained = c > 0 && row_ok;
     bool fast;  // every h carry of the tile was already there: no polling in the state loop
 
@@ -410,15 +409,22 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     }
 
     if (a.trace && tid == 0) tr_loop = gtime_ns();
+    // per-state pointers advance by NQ per trip (keeps 64-bit address arithmetic out of the loop body)
+    const unsigned long long* cin_p = cin;
+    const int coff = (c & 1) ? kMaxState : -kMaxState;  // the outgoing ring slot sits 16 slots after / before the incoming one
+    const float* a2_p = sm_A2 + rloc * kMaxState;      // sm_hin follows at a fixed distance
+    const int my_ck = c * CKPT + (sl + 1) / CKSEG - 1;  // checkpoint this lane's segment end belongs to (if any)
+    const bool ck_lane = row_ok && (sl + 1) % CKSEG == 0 && my_ck < a.nck;
+    float* x_p = xrow + (long)my_ck * N;
     NZ_UNROLL(NZ_FWD_UNROLL)
-    for (int n = 0; n < NP; n += NQ) {  // NQ independent states per trip (instruction-level parallelism)
+    for (int n = 0; n < NP; n += NQ, cin_p += NQ, a2_p += NQ, x_p += NQ) {  // NQ states per trip
       float hc[NQ], P[NQ], H[NQ];
       unsigned ctag[NQ];
       float av[NQ][M], bv[NQ][M];
       if (fast) {
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
-          hc[qi] = sm_hin[rloc * kMaxState + n + qi];
+          hc[qi] = a2_p[R * kMaxState + qi];
           ctag[qi] = (unsigned)c;
         }
       } else {
@@ -429,13 +435,13 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
         for (int qi = 1; qi < NQ; ++qi) {
           hc[qi] = 0.f;
           ctag[qi] = 0;
-          if (chained) slot_load(cin + n + qi, hc[qi], ctag[qi]);
+          if (chained) slot_load(cin_p + qi, hc[qi], ctag[qi]);
         }
-        if (chained && n + NQ < NP) slot_load(cin + n + NQ, cv_next, ct_next);
+        if (chained && n + NQ < NP) slot_load(cin_p + NQ, cv_next, ct_next);
       }
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
-        const float A2 = sm_A2[rloc * kMaxState + n + qi];
+        const float A2 = a2_p[qi];
         P[qi] = ex2_approx(A2 * dlsum);  // product of a over this lane's segment
         lds_seg<T, M, ROWB>(tB, n + qi, lp, bv[qi]);
 #pragma unroll
@@ -464,7 +470,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
         const unsigned long long w0 = (a.trace && tid == 0) ? gtime_ns() : 0;
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
-          while (ctag[qi] != (unsigned)c) slot_load(cin + n + qi, hc[qi], ctag[qi]);
+          while (ctag[qi] != (unsigned)c) slot_load(cin_p + qi, hc[qi], ctag[qi]);
         }
         if (a.trace && tid == 0) tr_wait += gtime_ns() - w0;
       }
@@ -473,13 +479,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
       for (int qi = 0; qi < NQ; ++qi) {
         h[qi] = ks_enter_up_w<RPW>(P[qi], H[qi], hc[qi]);
         const float hend = fmaf(P[qi], hc[qi], H[qi]);  // state at the end of this lane's segment
-        if (row_ok && n + qi < kMaxState) {
-          if (sl == LPR - 1) slot_store(cout + n + qi, hend, (unsigned)c + 1u);
-          if ((sl + 1) % CKSEG == 0 && n + qi < N) {
-            const int ck = c * CKPT + (sl + 1) / CKSEG - 1;
-            if (ck < a.nck) xrow[(long)ck * N + n + qi] = hend;
-          }
-        }
+        if (sl == LPR - 1 && row_ok) slot_store(const_cast<unsigned long long*>(cin_p) + coff + qi, hend, (unsigned)c + 1u);
+        if (ck_lane && n + qi < N) x_p[qi] = hend;
       }
 #pragma unroll
       for (int i = 0; i < M; ++i) {  // replay with the true carry-in; bv is overwritten by h_t
@@ -654,7 +655,6 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       dlfirst_next = x;
     }
     const unsigned long long* cin = a.carry + (rowg * 2 + ((c + 1) & 1)) * kMaxState;
-    unsigned long long* cout = a.carry + (rowg * 2 + (c & 1)) * kMaxState;
     const bool chained = c + 1 < a.nchunks && row_ok;
 
     bool fast;  // every dh carry of the tile was already there: no polling in the state loop
@@ -799,17 +799,21 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     }
     float* gsp = sm_gs + rloc * (LPR / 2) + (sl >> 1);
 
+    // per-state pointers advance by one per trip (keeps 64-bit address arithmetic out of the loop body)
+    const unsigned long long* cin_p = cin;
+    const int coff = (c & 1) ? kMaxState : -kMaxState;  // outgoing ring slot (c & 1) relative to the incoming one ((c + 1) & 1)
+    const float* a2_p = sm_A2 + rloc * kMaxState;  // sm_hc / sm_dhc follow at fixed distances
     NZ_UNROLL(NZ_BWD_UNROLL)
-    for (int n = 0; n < N; ++n, ++g) {
-      const float A2 = sm_A2[rloc * kMaxState + n];
+    for (int n = 0; n < N; ++n, ++g, ++cin_p, ++a2_p, gsp += R * LPR / 2) {
+      const float A2 = a2_p[0];
       const float An = A2 * kLn2;
-      const float hc = sm_hc[rloc * kMaxState + n];
-      float dhc = sm_dhc[rloc * kMaxState + n];
+      const float hc = a2_p[R * kMaxState];
+      float dhc = a2_p[2 * R * kMaxState];
       unsigned dtag = 0;
       if (!fast) {
         dhc = cv_next;
         dtag = ct_next;
-        if (chained && n + 1 < N) slot_load(cin + n + 1, cv_next, ct_next);
+        if (chained && n + 1 < N) slot_load(cin_p + 1, cv_next, ct_next);
       }
       float av[M], bv[M], cv[M], hh[M];
       [[maybe_unused]] float Bk[M];
@@ -850,11 +854,12 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         ks_down_w(Q, G, off * RPW);
       }
       if (!fast && chained) {
-        while (dtag != (unsigned)c + 2u) slot_load(cin + n, dhc, dtag);
+        while (dtag != (unsigned)c + 2u) slot_load(cin_p, dhc, dtag);
       }
       float h = ks_enter_up_w<RPW>(P, H, hc);
       float dh = ks_enter_down_w<RPW>(Q, G, dhc);
-      if (sl == 0 && row_ok) slot_store(cout + n, fmaf(Q, dhc, G), (unsigned)c + 1u);  // dh leaving the tile
+      if (sl == 0 && row_ok)  // dh leaving the tile
+        slot_store(const_cast<unsigned long long*>(cin_p) + coff, fmaf(Q, dhc, G), (unsigned)c + 1u);
       // the reducing warps of the previous state add its slabs while this state's scans are in flight
       if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
       // ---- replay both recurrences with the true carries ----
@@ -922,7 +927,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       {
         const float gsl = gs2.x + gs2.y;
         const float gsum = gsl + __shfl_down_sync(0xffffffffu, gsl, RPW);  // this segment + the next one
-        if ((sl & 1) == 0) gsp[n * (R * LPR / 2)] = gsum;
+        if ((sl & 1) == 0) gsp[0] = gsum;
       }
 
       // ---- dB/dC: every row writes its products into slab buffer g & 1 (reduced two states later at the latest) ----
