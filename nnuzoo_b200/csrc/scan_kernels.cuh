@@ -95,7 +95,7 @@ struct ScanCfg {
   static constexpr int SLAB = kBwd ? R * SLROW : 0;               // fp32 [R][TL]: one array of one slab buffer
   static constexpr int NRW = (2 * TL / 4) / 32;                   // warps reducing one state's dB + dC slabs
   static constexpr int GSB = kBwd ? kMaxState * R * (LPR / 2) * 4 : 0;  // dA partials [n][row][segment pair]
-  static constexpr int SMALL = 128 + (kBwd ? 3 : 2) * R * kMaxState * 4;
+  static constexpr int SMALL = 256 + (kBwd ? 3 : 2) * R * kMaxState * 4;
   static_assert(!kBwd || (NRW >= 1 && WARPS % NRW == 0), "reducer warps must tile the CTA");
   static_assert(RPW == 1 || RPW == 2, "one or two rows per warp");
   static_assert(TL % kCkpt == 0, "a tile is a whole number of checkpoint intervals");
@@ -136,7 +136,7 @@ __device__ __forceinline__ void slot_load(const unsigned long long* p, float& v,
 }
 
 struct TileId {
-  int b, g, rb, c, d0, rows_valid;
+  int b, g, rb, c, d0, rows_valid, pad0, pad1;  // 32 bytes: four of them sit in shared memory next to the ticket ring
 };
 template <int R, bool kBwd>
 __device__ __forceinline__ TileId decode_tile(const ScanKArgs& a, int t) {
@@ -248,7 +248,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
   uint8_t* tail = bcs + (kTMA ? 2 : 1) * Cfg::BC_TX;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);            // [0] rows, [1],[2] B/C stages
   volatile int* tk = reinterpret_cast<volatile int*>(tail + 32);  // ring of 4 tickets
-  float* sm_A2 = reinterpret_cast<float*>(tail + 128);
+  TileId* tq = reinterpret_cast<TileId*>(tail + 128);              // ... and their decoded tile coordinates
+  float* sm_A2 = reinterpret_cast<float*>(tail + 256);
   float* sm_hin = sm_A2 + R * kMaxState;  // h carried into the tile when the previous chunk had already finished
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -281,10 +282,13 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     fence_mbar_init();
     const int t0 = (int)atomicAdd(a.ticket, 1u);
     tk[0] = t0;
-    if (kTMA && t0 < a.ntiles) {
+    if (t0 < a.ntiles) {
       const TileId q = decode_tile<R, false>(a, t0);
-      issue_rows(q);
-      issue_bc(q, 0);
+      tq[0] = q;
+      if (kTMA) {
+        issue_rows(q);
+        issue_bc(q, 0);
+      }
     }
   }
   __syncthreads();
@@ -292,7 +296,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
   for (int k = 0;; ++k) {
     const int t = tk[k & 3];
     if (t >= a.ntiles) break;
-    const TileId q = decode_tile<R, false>(a, t);
+    const TileId q = tq[k & 3];  // decoded once by thread 0 when it claimed the ticket
     const int c = q.c, s = kTMA ? (k & 1) : 0;
     const bool row_ok = kTMA || rloc < q.rows_valid;  // the TMA path only runs whole row blocks
     const int d = q.d0 + (row_ok ? rloc : 0);
@@ -349,7 +353,10 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
           sm_A2[tid + j * NT] = a2pre[j];
           sm_hin[tid + j * NT] = hpre[j];
         }
-      if (tid == 0) tk[(k + 1) & 3] = (int)nxt;
+      if (tid == 0) {
+        tk[(k + 1) & 3] = (int)nxt;
+        if ((int)nxt < a.ntiles) tq[(k + 1) & 3] = decode_tile<R, false>(a, (int)nxt);
+      }
       fast = __syncthreads_and(all_in) != 0;
     }
     const long t0 = (long)c * TL + sl * M;
@@ -383,6 +390,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
         tk[(k + 1) & 3] = (int)nxt;
         if ((int)nxt < a.ntiles) {
           const TileId qn = decode_tile<R, false>(a, (int)nxt);
+          tq[(k + 1) & 3] = qn;
           issue_rows(qn);
           issue_bc(qn, (k + 1) & 1);
         }
@@ -557,7 +565,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   uint8_t* tail = reinterpret_cast<uint8_t*>(sm_gs) + Cfg::GSB;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // [0] rows, [1],[2] B/C stages, [3],[4] slab full, [5],[6] slab free
   volatile int* tk = reinterpret_cast<volatile int*>(tail + 64);
-  float* sm_A2 = reinterpret_cast<float*>(tail + 128);
+  TileId* tq = reinterpret_cast<TileId*>(tail + 128);
+  float* sm_A2 = reinterpret_cast<float*>(tail + 256);
   float* sm_hc = sm_A2 + R * kMaxState;   // h carried into the tile (forward checkpoints)
   float* sm_dhc = sm_hc + R * kMaxState;  // dh carried into the tile when the later chunk had already finished
 
@@ -605,10 +614,13 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     fence_mbar_init();
     const int t0 = (int)atomicAdd(a.ticket, 1u);
     tk[0] = t0;
-    if (kTMA && t0 < a.ntiles) {
+    if (t0 < a.ntiles) {
       const TileId q = decode_tile<R, true>(a, t0);
-      issue_rows(q);
-      issue_bc(q, 0);
+      tq[0] = q;
+      if (kTMA) {
+        issue_rows(q);
+        issue_bc(q, 0);
+      }
     }
   }
   __syncthreads();
@@ -618,7 +630,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   for (int k = 0;; ++k) {
     const int t = tk[k & 3];
     if (t >= a.ntiles) break;
-    const TileId q = decode_tile<R, true>(a, t);
+    const TileId q = tq[k & 3];  // decoded once by thread 0 when it claimed the ticket
     const int c = q.c, s = kTMA ? (k & 1) : 0;
     const bool row_ok = kTMA || rloc < q.rows_valid;  // the TMA path only runs whole row blocks
     const int d = q.d0 + (row_ok ? rloc : 0);
@@ -682,7 +694,10 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sm_hc[tid + j * NT] = hcpre[j];
           sm_dhc[tid + j * NT] = dhpre[j];
         }
-      if (tid == 0) tk[(k + 1) & 3] = (int)nxt;
+      if (tid == 0) {
+        tk[(k + 1) & 3] = (int)nxt;
+        if ((int)nxt < a.ntiles) tq[(k + 1) & 3] = decode_tile<R, true>(a, (int)nxt);
+      }
       fast = __syncthreads_and(all_in) != 0;
     }
     const long t0 = (long)c * TL + sl * M;
@@ -742,6 +757,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         tk[(k + 1) & 3] = (int)nxt;
         if ((int)nxt < a.ntiles) {
           const TileId qn = decode_tile<R, true>(a, (int)nxt);
+          tq[(k + 1) & 3] = qn;
           issue_rows(qn);
           issue_bc(qn, (k + 1) & 1);
         }
