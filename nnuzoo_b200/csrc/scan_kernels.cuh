@@ -168,6 +168,34 @@ __device__ __forceinline__ void coop_fill(uint8_t* tile, const T* base, long row
   }
 }
 
+// ---- explicit shared-space accesses (32-bit addresses: no generic-pointer arithmetic in the hot loops) ----
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float x) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(x) : "memory");
+}
+// Hide a loop-invariant value's recipe from the optimiser: at 128 registers ptxas otherwise
+// rematerialises it (address swizzles, the sum of dl) inside every trip of the state loop.
+__device__ __forceinline__ uint32_t keep(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+__device__ __forceinline__ float keep(float x) {
+  asm volatile("" : "+f"(x));
+  return x;
+}
+
 // A lane's M items out of a swizzled dense-row tile.  `pre[j]` = swz128(segoff + 16 j) is the lane's
 // swizzled in-row offset of its j-th 16-byte vector (loop invariant); a row adds row*ROWB to the
 // address and (row * ROWB/128) & 7 to the swizzle key -- the two never overlap because ROWB is a
@@ -178,18 +206,18 @@ struct LanePre {
   uint32_t pre[kVec];
   __device__ __forceinline__ explicit LanePre(uint32_t segoff) {
 #pragma unroll
-    for (int j = 0; j < kVec; ++j) pre[j] = swz128(segoff + 16u * j);
+    for (int j = 0; j < kVec; ++j) pre[j] = keep(swz128(segoff + 16u * j));
   }
 };
 template <typename T, int M, int ROWB>
-__device__ __forceinline__ void lds_seg(const uint8_t* tile, int row, const LanePre<M, T>& lp, float (&v)[M]) {
+__device__ __forceinline__ void lds_seg(uint32_t tile_s, int row, const LanePre<M, T>& lp, float (&v)[M]) {
   static_assert((ROWB & (ROWB - 1)) == 0 && ROWB >= 128 && ROWB <= 1024, "row pitch must be a power of two in [128, 1024]");
   constexpr int kPer = 16 / (int)sizeof(T);
   const uint32_t rowx = (((uint32_t)row * (ROWB / 128)) & 7u) << 4;
-  const uint8_t* base = tile + (uint32_t)row * ROWB;
+  const uint32_t base = tile_s + (uint32_t)row * ROWB;
 #pragma unroll
   for (int j = 0; j < LanePre<M, T>::kVec; ++j) {
-    unpack16<T>(*reinterpret_cast<const uint4*>(base + (lp.pre[j] ^ rowx)), &v[j * kPer]);
+    unpack16<T>(lds128(base + (lp.pre[j] ^ rowx)), &v[j * kPer]);
   }
 }
 
@@ -251,6 +279,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
   TileId* tq = reinterpret_cast<TileId*>(tail + 128);              // ... and their decoded tile coordinates
   float* sm_A2 = reinterpret_cast<float*>(tail + 256);
   float* sm_hin = sm_A2 + R * kMaxState;  // h carried into the tile when the previous chunk had already finished
+  const uint32_t rows_s = keep(smem_u32(rows)), bcs_s = rows_s + Cfg::ROWS_REGION;
+  const uint32_t a2_s0 = rows_s + (uint32_t)(reinterpret_cast<uint8_t*>(sm_A2) - rows);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sl = lane / RPW;                      // segment (time) index inside the row
@@ -363,9 +393,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     const int nvalid = (int)max(0L, min((long)M, a.L - t0));  // steps of this lane's segment inside the sequence
 
     float dlu[M], dl[M], y[M], zz[kHasZ ? M : 1];
-    lds_seg<T, M, ROWB>(rows, rloc, lp, dlu);
-    lds_seg<T, M, ROWB>(rows + ROWTILE, rloc, lp, dl);
-    if constexpr (kHasZ) lds_seg<T, M, ROWB>(rows + 2 * ROWTILE, rloc, lp, zz);
+    lds_seg<T, M, ROWB>(rows_s, rloc, lp, dlu);
+    lds_seg<T, M, ROWB>(rows_s + ROWTILE, rloc, lp, dl);
+    if constexpr (kHasZ) lds_seg<T, M, ROWB>(rows_s + 2 * ROWTILE, rloc, lp, zz);
     float dlsum = 0.f;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
@@ -397,8 +427,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
       }
       mbar_wait(&bars[1 + s], (k >> 1) & 1);
     }
-    const uint8_t* tB = bcs + s * Cfg::BC_TX;
-    const uint8_t* tC = tB + BCTILE;
+    const uint32_t tB = bcs_s + s * Cfg::BC_TX, tC = tB + BCTILE;
+    dlsum = keep(dlsum);
     T* outrow = reinterpret_cast<T*>(a.out) + (long)q.b * a.o_bs + (long)d * a.o_ds;
     float* xrow = a.x + rowg * (long)a.nck * N;
 
@@ -420,19 +450,19 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     // per-state pointers advance by NQ per trip (keeps 64-bit address arithmetic out of the loop body)
     const unsigned long long* cin_p = cin;
     const int coff = (c & 1) ? kMaxState : -kMaxState;  // the outgoing ring slot sits 16 slots after / before the incoming one
-    const float* a2_p = sm_A2 + rloc * kMaxState;      // sm_hin follows at a fixed distance
+    uint32_t a2_p = a2_s0 + rloc * (kMaxState * 4);    // sm_hin follows at a fixed distance
     const int my_ck = c * CKPT + (sl + 1) / CKSEG - 1;  // checkpoint this lane's segment end belongs to (if any)
     const bool ck_lane = row_ok && (sl + 1) % CKSEG == 0 && my_ck < a.nck;
     float* x_p = xrow + (long)my_ck * N;
     NZ_UNROLL(NZ_FWD_UNROLL)
-    for (int n = 0; n < NP; n += NQ, cin_p += NQ, a2_p += NQ, x_p += NQ) {  // NQ states per trip
+    for (int n = 0; n < NP; n += NQ, cin_p += NQ, a2_p += NQ * 4, x_p += NQ) {  // NQ states per trip
       float hc[NQ], P[NQ], H[NQ];
       unsigned ctag[NQ];
       float av[NQ][M], bv[NQ][M];
       if (fast) {
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
-          hc[qi] = a2_p[R * kMaxState + qi];
+          hc[qi] = lds32(a2_p + (R * kMaxState + qi) * 4);
           ctag[qi] = (unsigned)c;
         }
       } else {
@@ -449,7 +479,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
       }
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
-        const float A2 = a2_p[qi];
+        const float A2 = lds32(a2_p + qi * 4);
         P[qi] = ex2_approx(A2 * dlsum);  // product of a over this lane's segment
         lds_seg<T, M, ROWB>(tB, n + qi, lp, bv[qi]);
 #pragma unroll
@@ -569,6 +599,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   float* sm_A2 = reinterpret_cast<float*>(tail + 256);
   float* sm_hc = sm_A2 + R * kMaxState;   // h carried into the tile (forward checkpoints)
   float* sm_dhc = sm_hc + R * kMaxState;  // dh carried into the tile when the later chunk had already finished
+  const uint32_t rows_s = keep(smem_u32(rows)), bcs_s = rows_s + Cfg::ROWS_REGION;
+  const uint32_t slabs_s = rows_s + (uint32_t)(slabs - rows), gs_s0 = rows_s + (uint32_t)(reinterpret_cast<uint8_t*>(sm_gs) - rows);
+  const uint32_t a2_s0 = rows_s + (uint32_t)(reinterpret_cast<uint8_t*>(sm_A2) - rows);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int sl = lane / RPW;
@@ -581,11 +614,11 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   // bit 0 so that the 8 lanes of a quarter warp (four segments x two rows) hit 8 different bank groups.
   uint32_t slab_w[M / 4];
 #pragma unroll
-  for (int j = 0; j < M / 4; ++j) slab_w[j] = swz128(rloc * SLROW + sl * (M * 4) + 16 * j) ^ ((rloc & 1) ? 16u : 0u);
+  for (int j = 0; j < M / 4; ++j) slab_w[j] = keep(swz128(rloc * SLROW + sl * (M * 4) + 16 * j) ^ ((rloc & 1) ? 16u : 0u));
   // reducer role: lane -> one float4 (four time steps) of dB (red_arr 0) or dC (1)
   const int red_item = (warp % NRW) * 32 + lane;
   const int red_arr = red_item / QPA, red_q = red_item % QPA;
-  const uint32_t red_in = swz128((uint32_t)red_q * 16u);
+  const uint32_t red_in = keep(swz128((uint32_t)red_q * 16u));
 
   auto issue_rows = [&](const TileId& q) {
     mbar_arrive_expect_tx(&bars[0], Cfg::ROWS_TX);
@@ -705,16 +738,16 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
 
     float dl[M], dy[M], dlu[M], sB[M], ddl[M];
     float yv[kHasZ ? M : 1], dzf[kHasZ ? M : 1];
-    lds_seg<T, M, ROWB>(rows, rloc, lp, dlu);
-    lds_seg<T, M, ROWB>(rows + ROWTILE, rloc, lp, dl);
+    lds_seg<T, M, ROWB>(rows_s, rloc, lp, dlu);
+    lds_seg<T, M, ROWB>(rows_s + ROWTILE, rloc, lp, dl);
     // u is needed again only by the epilogue: park it in shared memory (the row tiles are refilled early)
 #pragma unroll
     for (int j = 0; j < M / 4; ++j)
       *reinterpret_cast<float4*>(ucopy + slab_w[j]) = make_float4(dlu[4 * j], dlu[4 * j + 1], dlu[4 * j + 2], dlu[4 * j + 3]);
-    lds_seg<T, M, ROWB>(rows + 2 * ROWTILE, rloc, lp, dy);
+    lds_seg<T, M, ROWB>(rows_s + 2 * ROWTILE, rloc, lp, dy);
     if constexpr (kHasZ) {
       float zz[M];
-      lds_seg<T, M, ROWB>(rows + 3 * ROWTILE, rloc, lp, zz);
+      lds_seg<T, M, ROWB>(rows_s + 3 * ROWTILE, rloc, lp, zz);
 #pragma unroll
       for (int i = 0; i < M; ++i) {
         const float sg = sigmoid_f(zz[i]);
@@ -742,7 +775,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     // of the later chunk for the last segment): a_{t+1} of the reverse recurrence at the segment end
     float dlnext = __shfl_down_sync(0xffffffffu, dl[0], RPW);
     if (sl == LPR - 1) dlnext = dlfirst_next;
-    const float qsum = dlsum - dl[0] + dlnext;  // sum of dl over (segment shifted by one step)
+    const float qsum = keep(dlsum - dl[0] + dlnext);  // sum of dl over (segment shifted by one step)
+    dlsum = keep(dlsum);
 
     if constexpr (kTMA) {
 #pragma unroll
@@ -764,8 +798,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       }
       mbar_wait(&bars[1 + s], (k >> 1) & 1);
     }
-    const uint8_t* tB = bcs + s * Cfg::BC_TX;
-    const uint8_t* tC = tB + BCTILE;
+    const uint32_t tB = bcs_s + s * Cfg::BC_TX, tC = tB + BCTILE;
     float* dG = (red_arr ? a.dC : a.dB) + (((long)q.b * a.ngroups + q.g) * N) * a.L + (long)c * TL + red_q * 4;
     const bool red_vec = a.vec_grad && (long)c * TL + red_q * 4 + 4 <= a.L;
 
@@ -773,14 +806,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     auto reduce_slab = [&](int n, unsigned gp) {
       const int bq = gp & 1;
       mbar_wait(&bars[3 + bq], (gp >> 1) & 1);
-      const uint8_t* sb = slabs + (bq * 2 + red_arr) * SLAB;
+      const uint32_t sb = slabs_s + (bq * 2 + red_arr) * SLAB;
       float2 lo = f2(0.f, 0.f), hi = f2(0.f, 0.f);
 #pragma unroll
       for (int r = 0; r < R; ++r) {  // row r adds r*SLROW to the address and its swizzle key / parity flip to the offset
         const uint32_t key = (uint32_t)((((r * (SLROW / 128)) & 7) << 4) ^ ((r & 1) ? 16 : 0));
-        const float4 v = *reinterpret_cast<const float4*>(sb + r * SLROW + (red_in ^ key));
-        lo = __fadd2_rn(lo, f2(v.x, v.y));
-        hi = __fadd2_rn(hi, f2(v.z, v.w));
+        const uint4 v = lds128(sb + r * SLROW + (red_in ^ key));
+        lo = __fadd2_rn(lo, f2(__uint_as_float(v.x), __uint_as_float(v.y)));
+        hi = __fadd2_rn(hi, f2(__uint_as_float(v.z), __uint_as_float(v.w)));
       }
       mbar_arrive(&bars[5 + bq]);
       float* dst = dG + (long)n * a.L;
@@ -813,18 +846,18 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       } while (tg != (unsigned)c + 2u);
       slot_load(cin, cv_next, ct_next);
     }
-    float* gsp = sm_gs + rloc * (LPR / 2) + (sl >> 1);
+    uint32_t gsp = gs_s0 + (rloc * (LPR / 2) + (sl >> 1)) * 4;
 
     // per-state pointers advance by one per trip (keeps 64-bit address arithmetic out of the loop body)
     const unsigned long long* cin_p = cin;
     const int coff = (c & 1) ? kMaxState : -kMaxState;  // outgoing ring slot (c & 1) relative to the incoming one ((c + 1) & 1)
-    const float* a2_p = sm_A2 + rloc * kMaxState;  // sm_hc / sm_dhc follow at fixed distances
+    uint32_t a2_p = a2_s0 + rloc * (kMaxState * 4);  // sm_hc / sm_dhc follow at fixed distances
     NZ_UNROLL(NZ_BWD_UNROLL)
-    for (int n = 0; n < N; ++n, ++g, ++cin_p, ++a2_p, gsp += R * LPR / 2) {
-      const float A2 = a2_p[0];
+    for (int n = 0; n < N; ++n, ++g, ++cin_p, a2_p += 4, gsp += R * LPR / 2 * 4) {
+      const float A2 = lds32(a2_p);
       const float An = A2 * kLn2;
-      const float hc = a2_p[R * kMaxState];
-      float dhc = a2_p[2 * R * kMaxState];
+      const float hc = lds32(a2_p + R * kMaxState * 4);
+      float dhc = lds32(a2_p + 2 * R * kMaxState * 4);
       unsigned dtag = 0;
       if (!fast) {
         dhc = cv_next;
@@ -943,17 +976,17 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       {
         const float gsl = gs2.x + gs2.y;
         const float gsum = gsl + __shfl_down_sync(0xffffffffu, gsl, RPW);  // this segment + the next one
-        if ((sl & 1) == 0) gsp[0] = gsum;
+        if ((sl & 1) == 0) sts32(gsp, gsum);
       }
 
       // ---- dB/dC: every row writes its products into slab buffer g & 1 (reduced two states later at the latest) ----
       if (g >= 2) mbar_wait(&bars[5 + (g & 1)], ((g >> 1) - 1) & 1);  // the buffer's previous content has been consumed
       {
-        uint8_t* sb = slabs + (g & 1) * (2 * SLAB);
+        const uint32_t sb = slabs_s + (g & 1) * (2 * SLAB);
 #pragma unroll
         for (int j = 0; j < M / 4; ++j) {
-          *reinterpret_cast<float4*>(sb + slab_w[j]) = make_float4(vB[4 * j], vB[4 * j + 1], vB[4 * j + 2], vB[4 * j + 3]);
-          *reinterpret_cast<float4*>(sb + SLAB + slab_w[j]) = make_float4(vC[4 * j], vC[4 * j + 1], vC[4 * j + 2], vC[4 * j + 3]);
+          sts128(sb + slab_w[j], vB[4 * j], vB[4 * j + 1], vB[4 * j + 2], vB[4 * j + 3]);
+          sts128(sb + SLAB + slab_w[j], vC[4 * j], vC[4 * j + 1], vC[4 * j + 2], vC[4 * j + 3]);
         }
       }
       mbar_arrive(&bars[3 + (g & 1)]);  // my part of slab(n) is written
