@@ -147,9 +147,10 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   a.nchunks = (int)((d->seqlen + tl - 1) / tl);
   a.nck = (int)nz_scan_num_chunks(d->seqlen);
   a.ntiles = a.nrb_total * a.nchunks;
-  // a dependent tile whose predecessor is still running starts `skew` states behind it; fewer row
-  // blocks than CTAs means deeper pipelines along L, which want a smaller skew
-  a.skew = a.nrb_total >= 24 ? 1 : 0;
+  // optional start skew: a dependent tile whose predecessor is still running may wait until that one is
+  // `skew` states ahead before it starts polling.  Measured (profiles/r01_kernel_tuning.md): every value
+  // >= 0 loses to not waiting at all (-1), so it stays an experiment knob.
+  a.skew = -1;
   if (const char* e = getenv("NZ_SKEW")) a.skew = atoi(e);  // tuning override
   a.ticket = reinterpret_cast<unsigned*>(d->workspace);
   a.carry = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d->workspace) + kWsHeader);

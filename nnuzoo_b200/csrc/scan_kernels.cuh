@@ -44,6 +44,9 @@
 #endif
 #define NZ_PRAGMA_(x) _Pragma(#x)
 #define NZ_UNROLL(n) NZ_PRAGMA_(unroll n)
+#ifndef NZ_BWD_REDUCE_LATE
+#define NZ_BWD_REDUCE_LATE 1  // reduce slab(n-1) 0: after the scans of state n, 1: before writing slab(n) (7.62 -> 7.27), 2: after it
+#endif
 #ifndef NZ_BWD_KEEPB
 #define NZ_BWD_KEEPB 0  // 1: keep B_t[n] in registers instead of re-reading the tile for sum_n dh*B (costs 8 registers)
 #endif
@@ -437,12 +440,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     float cv_next = 0.f;
     unsigned ct_next = 0;
     if (!fast && chained) {
-      const int nsk = min(a.skew, N - 1);
-      unsigned tg;
-      float dummy;
-      do {
-        slot_load(cin + nsk, dummy, tg);
-      } while (tg != (unsigned)c);
+      if (a.skew >= 0) {
+        const int nsk = min(a.skew, N - 1);
+        unsigned tg;
+        float dummy;
+        do {
+          slot_load(cin + nsk, dummy, tg);
+        } while (tg != (unsigned)c);
+      }
       slot_load(cin, cv_next, ct_next);
     }
 
@@ -838,12 +843,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     float cv_next = 0.f;
     unsigned ct_next = 0;
     if (!fast && chained) {
-      const int nsk = min(a.skew, N - 1);
-      unsigned tg;
-      float dummy;
-      do {
-        slot_load(cin + nsk, dummy, tg);
-      } while (tg != (unsigned)c + 2u);
+      if (a.skew >= 0) {
+        const int nsk = min(a.skew, N - 1);
+        unsigned tg;
+        float dummy;
+        do {
+          slot_load(cin + nsk, dummy, tg);
+        } while (tg != (unsigned)c + 2u);
+      }
       slot_load(cin, cv_next, ct_next);
     }
     uint32_t gsp = gs_s0 + (rloc * (LPR / 2) + (sl >> 1)) * 4;
@@ -909,8 +916,10 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       float dh = ks_enter_down_w<RPW>(Q, G, dhc);
       if (sl == 0 && row_ok)  // dh leaving the tile
         slot_store(const_cast<unsigned long long*>(cin_p) + coff, fmaf(Q, dhc, G), (unsigned)c + 1u);
+#if !NZ_BWD_REDUCE_LATE
       // the reducing warps of the previous state add its slabs while this state's scans are in flight
       if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
+#endif
       // ---- replay both recurrences with the true carries ----
       float dd[M];
 #pragma unroll
@@ -979,6 +988,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         if ((sl & 1) == 0) sts32(gsp, gsum);
       }
 
+#if NZ_BWD_REDUCE_LATE == 1
+      if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
+#endif
       // ---- dB/dC: every row writes its products into slab buffer g & 1 (reduced two states later at the latest) ----
       if (g >= 2) mbar_wait(&bars[5 + (g & 1)], ((g >> 1) - 1) & 1);  // the buffer's previous content has been consumed
       {
@@ -990,6 +1002,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         }
       }
       mbar_arrive(&bars[3 + (g & 1)]);  // my part of slab(n) is written
+#if NZ_BWD_REDUCE_LATE == 2
+      if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
+#endif
     }
     // the last state's slabs of this tile
     if ((int)((g - 1) % NGRP) == warp / NRW) reduce_slab(N - 1, g - 1);
