@@ -44,6 +44,9 @@
 #endif
 #define NZ_PRAGMA_(x) _Pragma(#x)
 #define NZ_UNROLL(n) NZ_PRAGMA_(unroll n)
+#ifndef NZ_FWD_SPLIT
+#define NZ_FWD_SPLIT 0  // 1: fold / replay a lane's segment as two independent half-chains (measured slower: 2.74 vs 2.60)
+#endif
 #ifndef NZ_BWD_REDUCE_LATE
 #define NZ_BWD_REDUCE_LATE 1  // reduce slab(n-1) 0: after the scans of state n, 1: before writing slab(n) (7.62 -> 7.27), 2: after it
 #endif
@@ -432,6 +435,16 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     }
     const uint32_t tB = bcs_s + s * Cfg::BC_TX, tC = tB + BCTILE;
     dlsum = keep(dlsum);
+    [[maybe_unused]] float dlsum_a = 0.f, dlsum_b = 0.f;
+#if NZ_FWD_SPLIT
+#pragma unroll
+    for (int i = 0; i < M / 2; ++i) {
+      dlsum_a += dl[i];
+      dlsum_b += dl[i + M / 2];
+    }
+    dlsum_a = keep(dlsum_a);
+    dlsum_b = keep(dlsum_b);
+#endif
     T* outrow = reinterpret_cast<T*>(a.out) + (long)q.b * a.o_bs + (long)d * a.o_ds;
     float* xrow = a.x + rowg * (long)a.nck * N;
 
@@ -462,6 +475,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     NZ_UNROLL(NZ_FWD_UNROLL)
     for (int n = 0; n < NP; n += NQ, cin_p += NQ, a2_p += NQ * 4, x_p += NQ) {  // NQ states per trip
       float hc[NQ], P[NQ], H[NQ];
+      [[maybe_unused]] float Pa[NQ], Pb[NQ];
       unsigned ctag[NQ];
       float av[NQ][M], bv[NQ][M];
       if (fast) {
@@ -485,7 +499,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
         const float A2 = lds32(a2_p + qi * 4);
+#if NZ_FWD_SPLIT
+        // the segment is folded / replayed as two independent half-chains (halves the serial FFMA latency)
+        Pa[qi] = ex2_approx(A2 * dlsum_a);  // product of a over the first / second half of the segment
+        P[qi] = Pa[qi] * ex2_approx(A2 * dlsum_b);
+        Pb[qi] = ex2_approx(A2 * dlsum_b);
+#else
         P[qi] = ex2_approx(A2 * dlsum);  // product of a over this lane's segment
+#endif
         lds_seg<T, M, ROWB>(tB, n + qi, lp, bv[qi]);
 #pragma unroll
         for (int kk = 0; kk < H2; ++kk) {
@@ -498,11 +519,27 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
         }
         H[qi] = 0.f;
       }
+#if NZ_FWD_SPLIT
+      float Ha[NQ];
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) Ha[qi] = 0.f;
+#pragma unroll
+      for (int i = 0; i < M / 2; ++i) {
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          Ha[qi] = fmaf(av[qi][i], Ha[qi], bv[qi][i]);
+          H[qi] = fmaf(av[qi][i + M / 2], H[qi], bv[qi][i + M / 2]);
+        }
+      }
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) H[qi] = fmaf(Pb[qi], Ha[qi], H[qi]);  // aggregate of the whole segment
+#else
 #pragma unroll
       for (int i = 0; i < M; ++i) {
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) H[qi] = fmaf(av[qi][i], H[qi], bv[qi][i]);
       }
+#endif
 #pragma unroll
       for (int off = 1; off < LPR; off <<= 1) {
 #pragma unroll
@@ -525,6 +562,19 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
         if (sl == LPR - 1 && row_ok) slot_store(const_cast<unsigned long long*>(cin_p) + coff + qi, hend, (unsigned)c + 1u);
         if (ck_lane && n + qi < N) x_p[qi] = hend;
       }
+#if NZ_FWD_SPLIT
+#pragma unroll
+      for (int qi = 0; qi < NQ; ++qi) Ha[qi] = fmaf(Pa[qi], h[qi], Ha[qi]);  // state in the middle of the segment
+#pragma unroll
+      for (int i = 0; i < M / 2; ++i) {  // replay both halves with their true carry-ins; bv is overwritten by h_t
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          h[qi] = fmaf(av[qi][i], h[qi], bv[qi][i]);
+          bv[qi][i] = h[qi];
+          Ha[qi] = fmaf(av[qi][i + M / 2], Ha[qi], bv[qi][i + M / 2]);
+          bv[qi][i + M / 2] = Ha[qi];
+        }
+#else
 #pragma unroll
       for (int i = 0; i < M; ++i) {  // replay with the true carry-in; bv is overwritten by h_t
 #pragma unroll
@@ -532,6 +582,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
           h[qi] = fmaf(av[qi][i], h[qi], bv[qi][i]);
           bv[qi][i] = h[qi];
         }
+#endif
       }
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {
