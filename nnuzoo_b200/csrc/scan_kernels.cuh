@@ -47,6 +47,15 @@
 #ifndef NZ_FWD_SPLIT
 #define NZ_FWD_SPLIT 0  // 1: fold / replay a lane's segment as two independent half-chains (measured slower: 2.74 vs 2.60)
 #endif
+#ifndef NZ_BWD_REDUCE_ALL
+#define NZ_BWD_REDUCE_ALL 0  // 1: every thread reduces one dB/dC element per state (balanced) instead of a rotating warp pair
+#endif
+#ifndef NZ_EXP_NOSLAB
+#define NZ_EXP_NOSLAB 0  // timing experiment (wrong results): the backward without the dB/dC slab hand-off and reduction
+#endif
+#ifndef NZ_EXP_NOHSCAN
+#define NZ_EXP_NOHSCAN 0  // timing experiment (wrong results): what the backward would cost without the h fold + scan
+#endif
 #ifndef NZ_BWD_REDUCE_LATE
 #define NZ_BWD_REDUCE_LATE 1  // reduce slab(n-1) 0: after the scans of state n, 1: before writing slab(n) (7.62 -> 7.27), 2: after it
 #endif
@@ -675,6 +684,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
   const int red_item = (warp % NRW) * 32 + lane;
   const int red_arr = red_item / QPA, red_q = red_item % QPA;
   const uint32_t red_in = keep(swz128((uint32_t)red_q * 16u));
+  [[maybe_unused]] const uint32_t red_in1 = keep(swz128((uint32_t)(tid % TL) * 4u));
 
   auto issue_rows = [&](const TileId& q) {
     mbar_arrive_expect_tx(&bars[0], Cfg::ROWS_TX);
@@ -698,8 +708,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     mbar_init(&bars[2], 1);
     mbar_init(&bars[3], NT);
     mbar_init(&bars[4], NT);
-    mbar_init(&bars[5], NRW * 32);
-    mbar_init(&bars[6], NRW * 32);
+    mbar_init(&bars[5], NZ_BWD_REDUCE_ALL ? NT : NRW * 32);
+    mbar_init(&bars[6], NZ_BWD_REDUCE_ALL ? NT : NRW * 32);
     fence_mbar_init();
     const int t0 = (int)atomicAdd(a.ticket, 1u);
     tk[0] = t0;
@@ -861,7 +871,31 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     // dB/dC of state n (CTA-local state counter gp): the NRW reducing warps add the R slab rows
     auto reduce_slab = [&](int n, unsigned gp) {
       const int bq = gp & 1;
+#if NZ_EXP_NOSLAB
+      return;  // timing experiment (wrong results): no slab hand-off, no reduction
+#endif
       mbar_wait(&bars[3 + bq], (gp >> 1) & 1);
+#if NZ_BWD_REDUCE_ALL
+      {  // every thread adds the R rows of ONE element (balanced: no warp carries a whole reduction)
+        static_assert(!NZ_BWD_REDUCE_ALL || 2 * TL == NT, "one dB/dC element per thread");
+        const int arr = tid / TL, tt = tid - arr * TL;
+        const uint32_t sb1 = slabs_s + (bq * 2 + arr) * SLAB;
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          const uint32_t k0 = (uint32_t)((((r * (SLROW / 128)) & 7) << 4));
+          const uint32_t k1 = (uint32_t)(((((r + 1) * (SLROW / 128)) & 7) << 4) ^ 16);
+          acc0 += lds32(sb1 + r * SLROW + (red_in1 ^ k0));
+          acc1 += lds32(sb1 + (r + 1) * SLROW + (red_in1 ^ k1));
+        }
+        mbar_arrive(&bars[5 + bq]);
+        if ((long)c * TL + tt < a.L) {
+          float* dst1 = (arr ? a.dC : a.dB) + (((long)q.b * a.ngroups + q.g) * N + n) * a.L + (long)c * TL + tt;
+          if (bpg == 1) *dst1 = acc0 + acc1; else atomicAdd(dst1, acc0 + acc1);
+        }
+        return;
+      }
+#endif
       const uint32_t sb = slabs_s + (bq * 2 + red_arr) * SLAB;
       float2 lo = f2(0.f, 0.f), hi = f2(0.f, 0.f);
 #pragma unroll
@@ -910,6 +944,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     const unsigned long long* cin_p = cin;
     const int coff = (c & 1) ? kMaxState : -kMaxState;  // outgoing ring slot (c & 1) relative to the incoming one ((c + 1) & 1)
     uint32_t a2_p = a2_s0 + rloc * (kMaxState * 4);  // sm_hc / sm_dhc follow at fixed distances
+    [[maybe_unused]] float exp_hin = 1.f;
+    [[maybe_unused]] const float* exp_x = a.x + rowg * a.nck * N + sl;
+    [[maybe_unused]] const int exp_max = a.nck * N - 16;
     NZ_UNROLL(NZ_BWD_UNROLL)
     for (int n = 0; n < N; ++n, ++g, ++cin_p, a2_p += 4, gsp += R * LPR / 2 * 4) {
       const float A2 = lds32(a2_p);
@@ -926,7 +963,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       [[maybe_unused]] float Bk[M];
       lds_seg<T, M, ROWB>(tB, n, lp, bv);
       lds_seg<T, M, ROWB>(tC, n, lp, cv);
+#if !NZ_EXP_NOHSCAN
       float P = ex2_approx(A2 * dlsum);    // prod a over the segment
+#endif
       float Q = ex2_approx(A2 * qsum);     // prod a over the segment shifted by one step
       const float anl = ex2_approx(A2 * dlnext);
       float cdy[M];
@@ -947,7 +986,17 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         cdy[2 * kk + 1] = c2.y;
       }
       // ---- both folds (independent chains): forward for h, reverse for dh ----
-      float H = 0.f, G = 0.f;
+      float G = 0.f;
+#if NZ_EXP_NOHSCAN
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+        const int j = M - 1 - i;
+        G = fmaf(j == M - 1 ? anl : av[j + 1], G, cdy[j]);
+      }
+#pragma unroll
+      for (int off = 1; off < LPR; off <<= 1) ks_down_w(Q, G, off * RPW);
+#else
+      float H = 0.f;
 #pragma unroll
       for (int i = 0; i < M; ++i) {
         H = fmaf(av[i], H, hh[i]);
@@ -960,16 +1009,22 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
         ks_up_w(P, H, off * RPW);
         ks_down_w(Q, G, off * RPW);
       }
+#endif
       if (!fast && chained) {
         while (dtag != (unsigned)c + 2u) slot_load(cin_p, dhc, dtag);
       }
+#if NZ_EXP_NOHSCAN
+      float h = hc * exp_hin;  // timing experiment only: a prefetched per-lane global load stands in
+      exp_hin = __ldg(exp_x + min((n + 1) * 16, exp_max));
+#else
       float h = ks_enter_up_w<RPW>(P, H, hc);
+#endif
       float dh = ks_enter_down_w<RPW>(Q, G, dhc);
       if (sl == 0 && row_ok)  // dh leaving the tile
         slot_store(const_cast<unsigned long long*>(cin_p) + coff, fmaf(Q, dhc, G), (unsigned)c + 1u);
 #if !NZ_BWD_REDUCE_LATE
       // the reducing warps of the previous state add its slabs while this state's scans are in flight
-      if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
+      if (n > 0 && (NZ_BWD_REDUCE_ALL || (int)((g - 1) % NGRP) == warp / NRW)) reduce_slab(n - 1, g - 1);
 #endif
       // ---- replay both recurrences with the true carries ----
       float dd[M];
@@ -1040,10 +1095,12 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       }
 
 #if NZ_BWD_REDUCE_LATE == 1
-      if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
+      if (n > 0 && (NZ_BWD_REDUCE_ALL || (int)((g - 1) % NGRP) == warp / NRW)) reduce_slab(n - 1, g - 1);
 #endif
       // ---- dB/dC: every row writes its products into slab buffer g & 1 (reduced two states later at the latest) ----
+#if !NZ_EXP_NOSLAB
       if (g >= 2) mbar_wait(&bars[5 + (g & 1)], ((g >> 1) - 1) & 1);  // the buffer's previous content has been consumed
+#endif
       {
         const uint32_t sb = slabs_s + (g & 1) * (2 * SLAB);
 #pragma unroll
@@ -1052,13 +1109,15 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sts128(sb + SLAB + slab_w[j], vC[4 * j], vC[4 * j + 1], vC[4 * j + 2], vC[4 * j + 3]);
         }
       }
+#if !NZ_EXP_NOSLAB
       mbar_arrive(&bars[3 + (g & 1)]);  // my part of slab(n) is written
+#endif
 #if NZ_BWD_REDUCE_LATE == 2
-      if (n > 0 && (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(n - 1, g - 1);
+      if (n > 0 && (NZ_BWD_REDUCE_ALL || (int)((g - 1) % NGRP) == warp / NRW)) reduce_slab(n - 1, g - 1);
 #endif
     }
     // the last state's slabs of this tile
-    if ((int)((g - 1) % NGRP) == warp / NRW) reduce_slab(N - 1, g - 1);
+    if (NZ_BWD_REDUCE_ALL || (int)((g - 1) % NGRP) == warp / NRW) reduce_slab(N - 1, g - 1);
 
     // ---- per-(row, t) epilogue ----
     const long rowlin = rowg * a.L;  // gradients are contiguous (batch, dim, L)
