@@ -145,6 +145,32 @@ int nz_cross_merge_bwd(const float* dy, float* d_out_y, int32_t batch, int32_t d
                        const int64_t* spatial, int32_t mode, void* stream);
 
 /*
+ * Depthwise causal conv1d (+ SiLU) of the 1-D Mamba block: out[b,d,l] = act(bias[d] + sum_k w[d,k] x[b,d,l-(W-1)+k])
+ * with x = 0 left of the sequence -- `self.act(self.conv1d(x)[..., :seqlen])`, mamba_simple.py:316-317, which the
+ * reference's fast path takes from causal_conv1d_cuda.causal_conv1d_fwd / _bwd (selective_scan_interface.py:177,
+ * :247-252).  W <= 4.  Strides in elements, innermost stride 1.  dx is written contiguous (batch, dim, L);
+ * dweight (dim, W) and dbias (dim) are ACCUMULATED INTO (caller zeroes), either may be NULL.
+ */
+typedef struct NzConv1dDesc {
+  int32_t batch, dim, width, dtype; /* dtype of x / out / dout / dx: NZ_F32 / NZ_BF16 / NZ_F16 */
+  int64_t seqlen;
+  int32_t silu;                     /* 1: SiLU activation fused, 0: plain convolution */
+  int32_t reserved0;
+  const void* x;                    /* (batch, dim, L) */
+  const float* weight;              /* (dim, W) fp32 */
+  const float* bias;                /* (dim) fp32 or NULL */
+  void* out;                        /* forward output (batch, dim, L) */
+  const void* dout;                 /* backward input */
+  void* dx;                         /* backward output, contiguous */
+  float* dweight;
+  float* dbias;
+  int64_t x_stride[2], out_stride[2], dout_stride[2]; /* batch, dim */
+} NzConv1dDesc;
+int nz_causal_conv1d_fwd(const NzConv1dDesc* desc, void* stream);
+int nz_causal_conv1d_bwd(const NzConv1dDesc* desc, void* stream);
+int64_t nz_sizeof_conv1d_desc(void);
+
+/*
  * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):
  * every pointer in `desc` is a HOST pointer, strides as above; the call stages host -> device,
  * runs nz_scan_fwd (and nz_scan_bwd when desc->dout != NULL) and copies the results back,

@@ -43,6 +43,19 @@ class NzScanDesc(ctypes.Structure):
     ]
 
 
+class NzConv1dDesc(ctypes.Structure):
+    """Field-for-field mirror of ``struct NzConv1dDesc`` in include/nnuzoo_b200.h."""
+
+    _fields_ = [
+        ("batch", _i32), ("dim", _i32), ("width", _i32), ("dtype", _i32),
+        ("seqlen", _i64),
+        ("silu", _i32), ("reserved0", _i32),
+        ("x", _vp), ("weight", _vp), ("bias", _vp), ("out", _vp), ("dout", _vp), ("dx", _vp),
+        ("dweight", _vp), ("dbias", _vp),
+        ("x_stride", _i64 * 2), ("out_stride", _i64 * 2), ("dout_stride", _i64 * 2),
+    ]
+
+
 _lib = None
 _lock = threading.Lock()
 _bound_device = {}
@@ -77,6 +90,13 @@ def lib():
                     fn = getattr(L, name)
                     fn.argtypes = [_vp, _vp, _i32, _i32, _i32, ctypes.POINTER(_i64), _i32, _vp]
                     fn.restype = ctypes.c_int
+                for name in ("nz_causal_conv1d_fwd", "nz_causal_conv1d_bwd"):
+                    fn = getattr(L, name)
+                    fn.argtypes = [ctypes.POINTER(NzConv1dDesc), _vp]
+                    fn.restype = ctypes.c_int
+                L.nz_sizeof_conv1d_desc.restype = _i64
+                if L.nz_sizeof_conv1d_desc() != ctypes.sizeof(NzConv1dDesc):
+                    raise NativeLibraryError("NzConv1dDesc layout differs between _native.py and the .so")
                 L.nz_last_error.restype = ctypes.c_char_p
                 L.nz_abi_version.restype = ctypes.c_int
                 L.nz_set_device.argtypes = [ctypes.c_int]

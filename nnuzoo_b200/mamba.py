@@ -11,8 +11,8 @@ parameter sets, which the reference creates unconditionally (:135-181).
                "v3"  : out + flip(out_b) + un-interleave(out_s)   (:213-249, SegMamba's tri-directional block)
 The scan is ``nnuzoo_b200.selective_scan_fn`` (K = 1 group, B/C (b, 1, N, L), z gate, delta_softplus,
 bias = dt_proj.bias -- exactly the call of MambaInnerFnNoOutProj.forward,
-selective_scan_interface.py:159-226).  The depthwise causal conv runs through cuDNN (``F.conv1d``); a fused
-causal_conv1d kernel is a "next" row.  The incremental ``step`` / inference cache
+selective_scan_interface.py:159-226).  The depthwise causal conv + SiLU is ``nnuzoo_b200.causal_conv1d_fn``
+(csrc/conv1d_kernels.cu, widths <= 4; wider kernels fall back to cuDNN).  The incremental ``step`` / inference cache
 (:359-446) is not used by nnUZoo and is not implemented.
 """
 from __future__ import annotations
@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .causal_conv1d import causal_conv1d_fn
 from .selective_scan_interface import selective_scan_fn
 
 
@@ -94,7 +95,10 @@ class Mamba(nn.Module):
     def _inner(self, xz, conv1d, x_proj, dt_proj, A_log, D):
         L = xz.shape[-1]
         x, z = xz.chunk(2, dim=1)
-        x = self.act(conv1d(x)[..., :L])                                     # causal depthwise conv + SiLU
+        if self.d_conv <= 4:   # causal depthwise conv + SiLU in one kernel (mamba_simple.py:319-324)
+            x = causal_conv1d_fn(x, conv1d.weight.squeeze(1), conv1d.bias, "silu")
+        else:
+            x = self.act(conv1d(x)[..., :L])
         x_dbl = F.linear(x.transpose(1, 2), x_proj.weight)                    # (b, l, R + 2N)
         dt, B, C = torch.split(x_dbl, [self.dt_rank, self.d_state, self.d_state], dim=-1)
         delta = F.linear(dt, dt_proj.weight).transpose(1, 2)                  # (b, d, l), L-contiguous after copy
