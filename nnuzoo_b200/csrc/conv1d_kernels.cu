@@ -106,11 +106,20 @@ __device__ __forceinline__ float dsilu_f(float p) {
   return s * (1.f + p * (1.f - s));
 }
 
+// Each thread owns CH consecutive 4-step chunks of one row (CH * 16 bytes of fp32, CH * 8 bytes of 16-bit data
+// per access stream) and slides the halo through registers, so every element is loaded once per thread.
+template <typename T>
+struct ConvCh {
+  static constexpr int CH = sizeof(T) == 4 ? 2 : 4;
+  static constexpr int STEPS = CH * kConvVec;  // steps per thread
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kConvThreads) conv1d_fwd_kernel(const ConvArgs a) {
-  const long nblk_l = (a.L + kConvThreads * kConvVec - 1) / (kConvThreads * kConvVec);
+  constexpr int CH = ConvCh<T>::CH, STEPS = ConvCh<T>::STEPS;
+  const long nblk_l = (a.L + kConvThreads * STEPS - 1) / (kConvThreads * STEPS);
   const long row = blockIdx.x / nblk_l;  // (batch, channel)
-  const long l0 = ((blockIdx.x % nblk_l) * kConvThreads + threadIdx.x) * kConvVec;
+  const long l0 = ((blockIdx.x % nblk_l) * kConvThreads + threadIdx.x) * STEPS;
   if (l0 >= a.L) return;
   const int b = (int)(row / a.dim), d = (int)(row % a.dim);
   const T* xr = reinterpret_cast<const T*>(a.x) + (long)b * a.x_bs + (long)d * a.x_ds;
@@ -119,35 +128,40 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_fwd_kernel(const ConvArgs
 #pragma unroll
   for (int k = 0; k < kConvMaxW; ++k) w[k] = k < a.width ? __ldg(a.w + (long)d * a.width + k) : 0.f;
   const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
-  float v[8];  // x[l0 - 4 .. l0 + 4)
-  load_window<T, 1, 0>(xr, l0, a.L, a.vec != 0, v);
+  float v[4 * (CH + 1)];  // x[l0 - 4 .. l0 + STEPS)
+  load_window<T, 1, CH - 1>(xr, l0, a.L, a.vec != 0, v);
   const int sh = kConvMaxW - a.width;  // taps are right-aligned: tap k multiplies x[l - (W-1) + k]
-  float o[kConvVec];
 #pragma unroll
-  for (int i = 0; i < kConvVec; ++i) {
-    float p = bias;
+  for (int cch = 0; cch < CH; ++cch) {
+    float o[kConvVec];
 #pragma unroll
-    for (int k = 0; k < kConvMaxW; ++k) {
-      const int kk = k - sh;  // index into w when width < kConvMaxW
-      if (kk >= 0) p = fmaf(w[kk], v[1 + i + k], p);
+    for (int i = 0; i < kConvVec; ++i) {
+      float p = bias;
+#pragma unroll
+      for (int k = 0; k < kConvMaxW; ++k) {
+        const int kk = k - sh;  // index into w when width < kConvMaxW
+        if (kk >= 0) p = fmaf(w[kk], v[4 * cch + 1 + i + k], p);
+      }
+      o[i] = a.silu ? silu_f(p) : p;
     }
-    o[i] = a.silu ? silu_f(p) : p;
-  }
-  if (a.vec) {
-    store4<T>(orow + l0, o);
-  } else {
+    const long lc = l0 + 4 * cch;
+    if (a.vec) {
+      if (lc < a.L) store4<T>(orow + lc, o);
+    } else {
 #pragma unroll
-    for (int i = 0; i < kConvVec; ++i)
-      if (l0 + i < a.L) orow[l0 + i] = Elem<T>::from_f(o[i]);
+      for (int i = 0; i < kConvVec; ++i)
+        if (lc + i < a.L) orow[lc + i] = Elem<T>::from_f(o[i]);
+    }
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const ConvArgs a) {
+  constexpr int CH = ConvCh<T>::CH, STEPS = ConvCh<T>::STEPS;
   __shared__ float red[kConvThreads / 32][kConvMaxW + 1];
-  const long nblk_l = (a.L + kConvThreads * kConvVec - 1) / (kConvThreads * kConvVec);
+  const long nblk_l = (a.L + kConvThreads * STEPS - 1) / (kConvThreads * STEPS);
   const long row = blockIdx.x / nblk_l;
-  const long l0 = ((blockIdx.x % nblk_l) * kConvThreads + threadIdx.x) * kConvVec;
+  const long l0 = ((blockIdx.x % nblk_l) * kConvThreads + threadIdx.x) * STEPS;
   const int b = (int)(row / a.dim), d = (int)(row % a.dim);
   const T* xr = reinterpret_cast<const T*>(a.x) + (long)b * a.x_bs + (long)d * a.x_ds;
   const T* gr = reinterpret_cast<const T*>(a.dout) + (long)b * a.do_bs + (long)d * a.do_ds;
@@ -160,14 +174,14 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const ConvArgs
   constexpr int HR = kConvMaxW - 1;                      // dx[l] needs dy[l .. l + W-1]
   float dwacc[kConvMaxW] = {0.f, 0.f, 0.f, 0.f}, dbacc = 0.f;
   if (l0 < a.L) {
-    float xw[12];                                          // x[l0 - 4 .. l0 + 8)
-    load_window<T, 1, 1>(xr, l0, a.L, a.vec != 0, xw);
+    float xw[4 * (CH + 2)];                                // x[l0 - 4 .. l0 + STEPS + 4)
+    load_window<T, 1, CH>(xr, l0, a.L, a.vec != 0, xw);
     const float* xv = xw + 1;                              // xv[j] = x[l0 - (W_max-1) + j]
-    float gw[8];                                           // dout[l0 .. l0 + 8)
-    load_window<T, 0, 1>(gr, l0, a.L, a.vec != 0, gw);
-    float dy[kConvVec + HR];                               // dy[l0 .. l0 + VEC + W-1)
+    float gw[4 * (CH + 1)];                                // dout[l0 .. l0 + STEPS + 4)
+    load_window<T, 0, CH>(gr, l0, a.L, a.vec != 0, gw);
+    float dy[STEPS + HR];                                  // dy[l0 .. l0 + STEPS + W-1)
 #pragma unroll
-    for (int i = 0; i < kConvVec + HR; ++i) {
+    for (int i = 0; i < STEPS + HR; ++i) {
       float g = gw[i];
       if (a.silu) {  // recompute the pre-activation at step l0 + i
         float p = bias;
@@ -180,28 +194,33 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const ConvArgs
       }
       dy[i] = g;
     }
-    float dxo[kConvVec];
 #pragma unroll
-    for (int i = 0; i < kConvVec; ++i) {
-      // dx[l] = sum_k w[k] * dy[l + (W-1) - k]
-      float acc = 0.f;
+    for (int cch = 0; cch < CH; ++cch) {
+      float dxo[kConvVec];
 #pragma unroll
-      for (int k = 0; k < kConvMaxW; ++k) {
-        const int kk = k - sh;
-        if (kk >= 0) acc = fmaf(w[kk], dy[i + (kConvMaxW - 1) - k], acc);
+      for (int ii = 0; ii < kConvVec; ++ii) {
+        const int i = 4 * cch + ii;
+        // dx[l] = sum_k w[k] * dy[l + (W-1) - k]
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < kConvMaxW; ++k) {
+          const int kk = k - sh;
+          if (kk >= 0) acc = fmaf(w[kk], dy[i + (kConvMaxW - 1) - k], acc);
+        }
+        dxo[ii] = acc;
+        // dw[k] += dy[l] * x[l - (W-1) + k],  dbias += dy[l]   (this thread owns steps l0 .. l0 + STEPS)
+        dbacc += dy[i];
+#pragma unroll
+        for (int k = 0; k < kConvMaxW; ++k) dwacc[k] = fmaf(dy[i], xv[i + k], dwacc[k]);
       }
-      dxo[i] = acc;
-      // dw[k] += dy[l] * x[l - (W-1) + k],  dbias += dy[l]   (this thread owns steps l0 .. l0 + VEC)
-      dbacc += dy[i];
+      const long lc = l0 + 4 * cch;
+      if (a.vec) {
+        if (lc < a.L) store4<T>(dxr + lc, dxo);
+      } else {
 #pragma unroll
-      for (int k = 0; k < kConvMaxW; ++k) dwacc[k] = fmaf(dy[i], xv[i + k], dwacc[k]);
-    }
-    if (a.vec) {
-      store4<T>(dxr + l0, dxo);
-    } else {
-#pragma unroll
-      for (int i = 0; i < kConvVec; ++i)
-        if (l0 + i < a.L) dxr[l0 + i] = Elem<T>::from_f(dxo[i]);
+        for (int ii = 0; ii < kConvVec; ++ii)
+          if (lc + ii < a.L) dxr[lc + ii] = Elem<T>::from_f(dxo[ii]);
+      }
     }
   }
   // CTA reduction of dw / dbias, then one atomic per (channel, tap) per CTA
@@ -268,7 +287,8 @@ int nz_causal_conv1d_fwd(const NzConv1dDesc* c, void* stream) {
   if (int rc = nz::conv_validate(c, false)) return rc;
   nz::ConvArgs a;
   nz::conv_fill(c, a);
-  const long nblk_l = (a.L + nz::kConvThreads * nz::kConvVec - 1) / (nz::kConvThreads * nz::kConvVec);
+  const int steps = c->dtype == NZ_F32 ? nz::ConvCh<float>::STEPS : nz::ConvCh<__half>::STEPS;
+  const long nblk_l = (a.L + nz::kConvThreads * steps - 1) / (nz::kConvThreads * steps);
   const unsigned grid = (unsigned)((long)a.batch * a.dim * nblk_l);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (c->dtype == NZ_F32) nz::conv1d_fwd_kernel<float><<<grid, nz::kConvThreads, 0, st>>>(a);
@@ -282,7 +302,8 @@ int nz_causal_conv1d_bwd(const NzConv1dDesc* c, void* stream) {
   if (int rc = nz::conv_validate(c, true)) return rc;
   nz::ConvArgs a;
   nz::conv_fill(c, a);
-  const long nblk_l = (a.L + nz::kConvThreads * nz::kConvVec - 1) / (nz::kConvThreads * nz::kConvVec);
+  const int steps = c->dtype == NZ_F32 ? nz::ConvCh<float>::STEPS : nz::ConvCh<__half>::STEPS;
+  const long nblk_l = (a.L + nz::kConvThreads * steps - 1) / (nz::kConvThreads * steps);
   const unsigned grid = (unsigned)((long)a.batch * a.dim * nblk_l);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (c->dtype == NZ_F32) nz::conv1d_bwd_kernel<float><<<grid, nz::kConvThreads, 0, st>>>(a);
