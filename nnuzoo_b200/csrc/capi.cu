@@ -151,6 +151,13 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   // `skew` states ahead before it starts polling.  Measured (profiles/r01_kernel_tuning.md): every value
   // >= 0 loses to not waiting at all (-1), so it stays an experiment knob.
   a.skew = -1;
+  // chain-limited launches (far fewer row blocks than the 2 resident CTAs per SM) claim tickets just in time
+  {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    a.claim_late = a.nrb_total <= sms / 2 ? 1 : 0;  // measured: 1.3-1.7x at 8 row blocks, neutral at 96, -5 % at 192
+  }
+  if (const char* e = getenv("NZ_CLAIM_LATE")) a.claim_late = atoi(e);  // tuning override
   if (const char* e = getenv("NZ_SKEW")) a.skew = atoi(e);  // tuning override
   a.ticket = reinterpret_cast<unsigned*>(d->workspace);
   a.carry = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d->workspace) + kWsHeader);

@@ -75,7 +75,8 @@ struct alignas(64) ScanKArgs {
   float *x, *dA, *dB, *dC, *dD, *dbias;
   unsigned long long* carry;  // [batch*dim][2][16] {value, tag} slots of the chained hand-off
   unsigned* ticket;           // dynamic tile counter (zeroed by the host before the launch)
-  unsigned long long* trace;  // optional (tools only): 6 words per tile {ticket, smid, t_start, t_loop, wait, t_end} in ns
+  unsigned long long* trace;  // optional (tools only): 8 words per tile {ticket, smid, t_start, t_loop, wait, t_end,
+                              // t state-0 carry received, t last-state carry received} in ns
   long L;
   long u_bs, u_ds, dl_bs, dl_ds, z_bs, z_ds, o_bs, o_ds, do_bs, do_ds;
   long B_bs, B_gs, B_ns, C_bs, C_gs, C_ns, A_ds;
@@ -86,6 +87,10 @@ struct alignas(64) ScanKArgs {
   int nck;        // checkpoints along L (ceil(L / kCkpt))
   int ntiles;     // nrb_total * nchunks
   int softplus;
+  int claim_late;  // 1: claim the next ticket at the END of a tile instead of one tile ahead.  With fewer row
+                   // blocks than CTA slots every tile waits on its predecessor; a ticket claimed early then
+                   // sits idle in a busy CTA while later tiles of its chain already occupy other CTAs
+                   // (priority inversion: the whole chain stalls until that CTA comes round)
   int skew;      // states the later chunk's tile must be ahead before a dependent tile starts polling
   int vec_out;   // out rows 16-byte aligned -> vector stores
   int vec_grad;  // du/ddelta/dz and dB/dC rows 16-byte aligned
@@ -148,6 +153,14 @@ __device__ __forceinline__ void slot_load(const unsigned long long* p, float& v,
   unsigned bits;
   asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(bits), "=r"(tag) : "l"(p) : "memory");
   v = __uint_as_float(bits);
+}
+
+// Poll a hand-off slot until it carries `expect`.  (Backing off with nanosleep when the slot's current tag shows
+// that the producer is several tiles away was measured and rejected: no gain on chain-bound shapes -- polling
+// traffic is not what limits them -- and 30 % slower on cfg 1, where the producer is only two tiles away.)
+template <bool kDescending>
+__device__ __forceinline__ void slot_wait(const unsigned long long* p, unsigned expect, float& v, unsigned& tag) {
+  while (tag != expect) slot_load(p, v, tag);
 }
 
 struct TileId {
@@ -350,8 +363,8 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     // spread of one tile duration, so a tile's predecessor along L is almost always already running);
     // its B/C stage is free, its row tiles are requested once this tile's rows sit in registers.
     unsigned nxt = 0;
-    if (tid == 0) nxt = atomicAdd(a.ticket, 1u);
-    unsigned long long tr_start = 0, tr_loop = 0, tr_wait = 0;
+    if (tid == 0 && !a.claim_late) nxt = atomicAdd(a.ticket, 1u);
+    unsigned long long tr_start = 0, tr_loop = 0, tr_wait = 0, tr_recv0 = 0, tr_recvN = 0;
     if (a.trace && tid == 0) tr_start = gtime_ns();
 
     const float Dv = a.D ? __ldg(a.D + d) : 0.f;
@@ -398,7 +411,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
           sm_A2[tid + j * NT] = a2pre[j];
           sm_hin[tid + j * NT] = hpre[j];
         }
-      if (tid == 0) {
+      if (tid == 0 && !a.claim_late) {
         tk[(k + 1) & 3] = (int)nxt;
         if ((int)nxt < a.ntiles) tq[(k + 1) & 3] = decode_tile<R, false>(a, (int)nxt);
       }
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
         }
       // the row values now live in registers: request the next ticket's tiles (rows + the free B/C stage)
       fast = __syncthreads_and(all_in) != 0;
-      if (tid == 0) {
+      if (tid == 0 && !a.claim_late) {
         tk[(k + 1) & 3] = (int)nxt;
         if ((int)nxt < a.ntiles) {
           const TileId qn = decode_tile<R, false>(a, (int)nxt);
@@ -559,9 +572,14 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
         const unsigned long long w0 = (a.trace && tid == 0) ? gtime_ns() : 0;
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
-          while (ctag[qi] != (unsigned)c) slot_load(cin_p + qi, hc[qi], ctag[qi]);
+          slot_wait<false>(cin_p + qi, (unsigned)c, hc[qi], ctag[qi]);
         }
-        if (a.trace && tid == 0) tr_wait += gtime_ns() - w0;
+        if (a.trace && tid == 0) {
+          const unsigned long long w1 = gtime_ns();
+          tr_wait += w1 - w0;
+          if (n == 0) tr_recv0 = w1;
+          tr_recvN = w1;
+        }
       }
       float h[NQ];
 #pragma unroll
@@ -613,7 +631,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
     }
     if (row_ok) stg_items<T, M>(outrow, y, t0, a.L, a.vec_out != 0);
     if (a.trace && tid == 0) {
-      unsigned long long* tr = a.trace + (long)t * 6;
+      unsigned long long* tr = a.trace + (long)t * 8;
+      tr[6] = tr_recv0;
+      tr[7] = tr_recvN;
       tr[0] = (unsigned long long)t | ((unsigned long long)fast << 32);
       tr[1] = smid();
       tr[2] = tr_start;
@@ -624,7 +644,22 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
 
     // every warp is done with this tile's B/C stage, sm_A2 and sm_hin
     __syncthreads();
-    if (!kTMA) __syncthreads();
+    if (a.claim_late) {  // few row blocks, long L: claim just in time (see ScanKArgs::claim_late)
+      if (tid == 0) {
+        nxt = atomicAdd(a.ticket, 1u);
+        tk[(k + 1) & 3] = (int)nxt;
+        if ((int)nxt < a.ntiles) {
+          const TileId qn = decode_tile<R, false>(a, (int)nxt);
+          tq[(k + 1) & 3] = qn;
+          if (kTMA) {
+            issue_rows(qn);
+            issue_bc(qn, (k + 1) & 1);
+          }
+        }
+      }
+      __syncthreads();
+    }
+
   }
 }
 
@@ -736,7 +771,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
     const long rowg = (long)q.b * a.dim + d;
     const int bpg = a.nrb;
     unsigned nxt = 0;  // the next ticket, claimed one tile ahead (see the forward kernel)
-    if (tid == 0) nxt = atomicAdd(a.ticket, 1u);
+    if (tid == 0 && !a.claim_late) nxt = atomicAdd(a.ticket, 1u);
 
     const float Dv = a.D ? __ldg(a.D + d) : 0.f;
     const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
@@ -793,7 +828,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sm_hc[tid + j * NT] = hcpre[j];
           sm_dhc[tid + j * NT] = dhpre[j];
         }
-      if (tid == 0) {
+      if (tid == 0 && !a.claim_late) {
         tk[(k + 1) & 3] = (int)nxt;
         if ((int)nxt < a.ntiles) tq[(k + 1) & 3] = decode_tile<R, true>(a, (int)nxt);
       }
@@ -853,7 +888,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
           sm_dhc[tid + j * NT] = dhpre[j];
         }
       fast = __syncthreads_and(all_in) != 0;  // row values are in registers: request the next ticket's tiles
-      if (tid == 0) {
+      if (tid == 0 && !a.claim_late) {
         tk[(k + 1) & 3] = (int)nxt;
         if ((int)nxt < a.ntiles) {
           const TileId qn = decode_tile<R, true>(a, (int)nxt);
@@ -1011,7 +1046,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
       }
 #endif
       if (!fast && chained) {
-        while (dtag != (unsigned)c + 2u) slot_load(cin_p, dhc, dtag);
+        slot_wait<true>(cin_p, (unsigned)c + 2u, dhc, dtag);
       }
 #if NZ_EXP_NOHSCAN
       float h = hc * exp_hin;  // timing experiment only: a prefetched per-lane global load stands in
@@ -1161,6 +1196,22 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
 
     // every warp is done with this tile's B/C stage, sm_A2 / sm_hc / sm_dhc and has written its dA partials
     __syncthreads();
+    if (a.claim_late) {  // few row blocks, long L: claim just in time (see ScanKArgs::claim_late)
+      if (tid == 0) {
+        nxt = atomicAdd(a.ticket, 1u);
+        tk[(k + 1) & 3] = (int)nxt;
+        if ((int)nxt < a.ntiles) {
+          const TileId qn = decode_tile<R, true>(a, (int)nxt);
+          tq[(k + 1) & 3] = qn;
+          if (kTMA) {
+            issue_rows(qn);
+            issue_bc(qn, (k + 1) & 1);
+          }
+        }
+      }
+      __syncthreads();
+    }
+
 #pragma unroll
     for (int j = 0; j < APT; ++j) {
       const int i = tid + j * NT, r = i % R, n = i / R;  // consecutive threads: consecutive rows (64-byte pitch)

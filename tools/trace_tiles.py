@@ -30,13 +30,13 @@ def main():
     nrb = batch * G * ((kd // G + rows_per_tile - 1) // rows_per_tile)
     nch = (L + tl - 1) // tl
     ntiles = nrb * nch
-    trace = torch.zeros(ntiles * 6, dtype=torch.int64, device=dev)
+    trace = torch.zeros(ntiles * 8, dtype=torch.int64, device=dev)
     for it in range(3):
         lib.nz_debug_set_trace(ctypes.c_void_p(trace.data_ptr() if it == 2 else 0))
         nnuzoo_b200.selective_scan_fn(u, dl, A, B, C, D, None, bias, True)
         torch.cuda.synchronize()
     lib.nz_debug_set_trace(None)
-    t = trace.cpu().numpy().reshape(ntiles, 6)
+    t = trace.cpu().numpy().reshape(ntiles, 8)
     ticket = t[:, 0] & 0xffffffff
     fast = t[:, 0] >> 32
     t0 = t[:, 2].min()
@@ -60,6 +60,15 @@ def main():
     lag_e = st[nrb:] - en[:-nrb]
     print(f"start(tile) - start(pred): mean {lag_s.mean() / 1e3:.2f} us  p10 {np.percentile(lag_s, 10) / 1e3:.2f}  p90 {np.percentile(lag_s, 90) / 1e3:.2f}")
     print(f"start(tile) - end(pred):   mean {lag_e.mean() / 1e3:.2f} us  p10 {np.percentile(lag_e, 10) / 1e3:.2f}  p90 {np.percentile(lag_e, 90) / 1e3:.2f}")
+    # hop latency along a chain: when tile c+1 received the state-0 / last-state carry relative to tile c
+    r0, rN = t[:, 6][order] - t0, t[:, 7][order] - t0
+    ok = (t[:, 6][order][nrb:] > 0) & (t[:, 6][order][:-nrb] > 0)
+    if ok.any():
+        h0 = (r0[nrb:] - r0[:-nrb])[ok]
+        hN = (rN[nrb:] - rN[:-nrb])[ok]
+        print(f"hop (carry-received time, tile c+1 minus tile c): state 0 mean {h0.mean() / 1e3:.2f} us p50 {np.percentile(h0, 50) / 1e3:.2f}  "
+              f"last state mean {hN.mean() / 1e3:.2f} us p50 {np.percentile(hN, 50) / 1e3:.2f};  "
+              f"in-tile state-0 -> last-state span mean {((rN - r0)[t[:, 6][order] > 0]).mean() / 1e3:.2f} us")
     sm = t[:, 1]
     per_sm = np.bincount(sm.astype(int))
     print(f"tiles per SM: min {per_sm[per_sm > 0].min()} max {per_sm.max()}")
