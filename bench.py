@@ -353,6 +353,46 @@ def e2e_run(dev, stream, steps, warmup):
     return dt, h2d, d2h
 
 
+def train_run(dev, world, steps, warmup, per_gpu_batch):
+    """The second half of BASELINE.json's metric: SS2D2Net (M2Net) training patches/s -- full optimisation steps
+    (H2D of the pinned batch, bf16-autocast forward, Dice+CE deep-supervision loss, backward with the DDP gradient
+    all-reduce over NCCL, clip, AdamW, loss read back) through nnuzoo_b200.train.Trainer.  Weak scaling: every rank
+    trains ``per_gpu_batch`` patches of 1x512x512, like the scan part of this line."""
+    import torch
+
+    from nnuzoo_b200 import _native
+    from nnuzoo_b200.m2net import get_m2net
+    from nnuzoo_b200.train import Trainer, synthetic_batch
+
+    torch.manual_seed(0)
+    trainer = Trainer(get_m2net(1, 4, True).train(), dev)
+    data, targets = synthetic_batch(per_gpu_batch, 1, 4, seed=17 + dev.index)
+    h2d = data.numel() * data.element_size() + sum(t.numel() * t.element_size() for t in targets)
+    for _ in range(warmup):
+        trainer.train_step(data, targets)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+    n0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss = None
+    for _ in range(steps):
+        loss = float(trainer.train_step(data, targets).item())     # D2H read of the step's result
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = max_over_ranks(e0.elapsed_time(e1) / steps, dev, world)
+    return {"patches_per_s": world * per_gpu_batch / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms,
+            "per_gpu_batch": per_gpu_batch, "global_batch": world * per_gpu_batch, "scaling": "weak",
+            "steps": steps, "warmup": warmup, "autocast": "bf16", "loss": loss,
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+            "our_kernel_launches_per_step": (_native.launch_count() - n0) // steps,
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
+            "what": "M2Net(1->4 classes, deep supervision) full training step via nnuzoo_b200.train.Trainer; "
+                    "DDP (NCCL all-reduce) when n_gpus > 1"}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -412,6 +452,14 @@ def run_gpu_arm(args):
                    "api": "nz_scan_fwd_bwd_host (include/nnuzoo_b200.h), pinned host buffers"}
         except Exception as ex:  # report, never fake
             e2e = {"value": None, "unit": "GB/s", "error": repr(ex)[:300]}
+    train = None
+    if not args.no_train:
+        del wl.u, wl.delta, wl.dout, wl.Bm, wl.Cm, wl.out, wl.du, wl.dd, wl.dB, wl.dC, wl.x
+        torch.cuda.empty_cache()
+        try:
+            train = train_run(dev, world, args.train_steps, 2, args.train_batch)
+        except Exception as ex:  # report, never fake
+            train = {"patches_per_s": None, "error": repr(ex)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_sample_run(1, 1)
         cpu = {"value": r["gbps"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
@@ -430,7 +478,7 @@ def run_gpu_arm(args):
                                    "128 steps; all 80 launches per step; algorithmic bytes 4*(5E+4S) per launch, "
                                    "achieved = sum of bytes / sum of CUDA-event durations of those launches)",
                          "share_of_step": bwd_ms / (ms_per_step * args.steps)},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "train": train, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
@@ -446,6 +494,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--train-batch", type=int, default=BATCH, help="per-GPU batch of the M2Net training leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

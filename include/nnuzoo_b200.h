@@ -171,6 +171,18 @@ int nz_causal_conv1d_bwd(const NzConv1dDesc* desc, void* stream);
 int64_t nz_sizeof_conv1d_desc(void);
 
 /*
+ * Weight gradient of SS2D's per-direction projections (the einsums at m2net.py:179 and :182, whose autograd
+ * backward the reference leaves to a library GEMM):
+ *     dW[k, m, n] += sum_{b, l} G[b, k, m, l] * X[b, k, n, l]
+ * x_proj: G = d x_dbl (B, K, R+2N, L), X = xs (B, K, D, L), dW (K, R+2N, D);
+ * dt_proj: G = d dts (B, K, D, L), X = the dt rows of x_dbl (B, K, R, L) as the strided split view, dW (K, D, R).
+ * g_stride / x_stride: element strides of (batch, direction, row); the sequence stride is 1.  dW is fp32,
+ * contiguous and ACCUMULATED INTO (caller zeroes).  M * N <= 10240.
+ */
+int nz_proj_wgrad(const void* G, const void* X, float* dW, int32_t g_dtype, int32_t x_dtype, int32_t batch, int32_t K,
+                  int32_t M, int32_t N, int64_t L, const int64_t* g_stride, const int64_t* x_stride, void* stream);
+
+/*
  * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):
  * every pointer in `desc` is a HOST pointer, strides as above; the call stages host -> device,
  * runs nz_scan_fwd (and nz_scan_bwd when desc->dout != NULL) and copies the results back,

@@ -94,6 +94,9 @@ def lib():
                     fn = getattr(L, name)
                     fn.argtypes = [ctypes.POINTER(NzConv1dDesc), _vp]
                     fn.restype = ctypes.c_int
+                L.nz_proj_wgrad.argtypes = [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i64,
+                                            ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]
+                L.nz_proj_wgrad.restype = ctypes.c_int
                 L.nz_sizeof_conv1d_desc.restype = _i64
                 if L.nz_sizeof_conv1d_desc() != ctypes.sizeof(NzConv1dDesc):
                     raise NativeLibraryError("NzConv1dDesc layout differs between _native.py and the .so")

@@ -29,6 +29,13 @@ static int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+void set_error(const char* fmt, ...) {  // for the other translation units
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static size_t esize(int dtype) { return dtype == NZ_F32 ? 4 : 2; }

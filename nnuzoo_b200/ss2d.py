@@ -9,7 +9,9 @@ Differences are confined to *how* forward_core executes:
   * CrossScan / CrossMerge are single bit-exact CUDA kernels (nnuzoo_b200.cross_scan) instead of
     stack / flip / transpose-contiguous chains;
   * the scan is nnuzoo_b200.selective_scan_fn (no mamba_ssm dependency);
-  * B/C are handed to the scan as the strided split views they are (no .contiguous()).
+  * B/C are handed to the scan as the strided split views they are (no .contiguous());
+  * the two projection einsums run as batched GEMMs whose weight gradient is our own reduction kernel
+    (nnuzoo_b200.proj).
 """
 from __future__ import annotations
 
@@ -20,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .cross_scan import cross_merge, cross_scan
+from .proj import grouped_proj
 from .selective_scan_interface import selective_scan_fn
 
 
@@ -113,9 +116,9 @@ class _CrossScanSSM(nn.Module):
         K, N, R = self.k, self.d_state, self.dt_rank
         xs = cross_scan(x)                                                    # (B, K, D, L)
         L = xs.shape[-1]
-        x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, self.x_proj_weight)          # m2net.py:179
+        x_dbl = grouped_proj(xs, self.x_proj_weight)            # einsum "b k d l, k c d -> b k c l", m2net.py:179
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                                  # :181
-        dts = torch.einsum("b k r l, k d r -> b k d l", dts, self.dt_projs_weight)          # :182
+        dts = grouped_proj(dts, self.dt_projs_weight)           # einsum "b k r l, k d r -> b k d l", :182
         out_y = self.selective_scan(
             xs.float().view(bsz, -1, L), dts.contiguous().float().view(bsz, -1, L),        # :185-186
             -torch.exp(self.A_logs.float()).view(-1, N),                                    # :190

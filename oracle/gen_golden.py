@@ -15,6 +15,10 @@ What is recorded (all seeds fixed, sizes tiny so the fixtures stay small):
                 SS2D (m2net.py:39-225) and SSND 2-D / 3-D (ssnd2net.py:73-318) modules, with the
                 reference's selective_scan_ref as the scan.
   module_mamba_*.npz: the vendored Mamba block (seg_mamba/mamba_simple.py:37-357), bimamba none / v2 / v3.
+  module_m2net_64x32.npz: the whole reference ``M2Net`` (m2net.py:805-971; 80 SS2D scans) in eval mode on a
+                (2, 1, 64, 32) input, parameters from oracle/fill.py (seeded, regenerated on both sides):
+                input, the 7 deep-supervision outputs, input gradient, per-parameter gradient norms and a
+                few whole parameter gradients.
   MANIFEST.json: case list plus the agreement of oracle/torch_port.py and oracle/scan_oracle.c with
                 the verbatim reference at generation time.
 """
@@ -236,6 +240,42 @@ def gen_mamba(manifest):
         manifest["module"][name] = dict(x_shape=list(xshape), y_abs_mean=float(y.abs().mean()), bimamba_type=kind)
 
 
+M2NET_FULL_GRADS = ("stage1.vssm_encoder.layers.0.blocks.0.self_attention.A_logs",
+                    "stage1.vssm_encoder.layers.0.blocks.0.self_attention.x_proj_weight",
+                    "stage1d.vssm_decoder.stages.5.blocks.0.self_attention.dt_projs_bias",
+                    "stage3.vssm_encoder.layers.2.blocks.0.self_attention.Ds",
+                    "stage4d.vssm_decoder.concat_back_dim.0.weight", "side3.weight", "outconv.weight")
+
+
+def gen_m2net(manifest):
+    from oracle.fill import deterministic_fill
+    m2 = ref_loader.m2net()
+    torch.manual_seed(500)
+    net = m2.M2Net(1, 4, True).eval()
+    deterministic_fill(net, 7)
+    x = torch.randn(2, 1, 64, 32, requires_grad=True)
+    outs = net(x)
+    gys = [torch.randn_like(o) for o in outs]
+    torch.autograd.backward(list(outs), gys)
+    rec = {"x": _np(x), "gx": _np(x.grad)}
+    for i, (o, g) in enumerate(zip(outs, gys)):
+        rec[f"d{i}"] = _np(o)
+        rec[f"gd{i}"] = _np(g)
+    names, norms = [], []
+    for k, p in sorted(net.named_parameters()):
+        names.append(k)
+        norms.append(0.0 if p.grad is None else float(p.grad.double().norm()))
+    rec["grad_norm_names"] = np.array(names)
+    rec["grad_norms"] = np.array(norms, np.float64)
+    params = dict(net.named_parameters())
+    for k in M2NET_FULL_GRADS:
+        rec["gp_" + k] = _np(params[k].grad)
+    np.savez_compressed(os.path.join(GOLD, "module_m2net_64x32.npz"), **rec)
+    manifest["module"]["module_m2net_64x32"] = dict(
+        x_shape=[2, 1, 64, 32], fill_seed=7, n_params=int(sum(p.numel() for p in net.parameters())),
+        unused_params=int(sum(1 for n in norms if n == 0.0)), d0_abs_mean=float(outs[0].abs().mean()))
+
+
 def main():
     assert ref_loader.available(), "run in the build container: /root/reference is required"
     os.makedirs(GOLD, exist_ok=True)
@@ -247,6 +287,7 @@ def main():
     gen_cross(manifest)
     gen_module(manifest)
     gen_mamba(manifest)
+    gen_m2net(manifest)
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print(json.dumps(manifest, indent=1, sort_keys=True))
