@@ -393,6 +393,39 @@ def train_run(dev, world, steps, warmup, per_gpu_batch):
                     "DDP (NCCL all-reduce) when n_gpus > 1"}
 
 
+def infer_run(dev, world, slices, tile_batch):
+    """BASELINE configs[4]: sliding-window inference of SS2D2Net over a synthetic (1, slices, 512, 512) volume, 2-D
+    tiles of 512x512 (step 0.5), mirroring over both axes (4 forwards per tile, stacked), gaussian-weighted fp16
+    accumulators; tiles sharded ``rank::world`` and merged with one all-reduce per accumulator (strong scaling: one
+    volume whatever N).  Timed: volume already on the device -> merged logits on the device."""
+    import torch
+
+    from nnuzoo_b200.m2net import get_m2net
+    from nnuzoo_b200.predict import SlidingWindowPredictor
+
+    torch.manual_seed(0)
+    net = get_m2net(1, 4, False)
+    pred = SlidingWindowPredictor(net, (512, 512), 4, dev, tile_batch=tile_batch)
+    g = torch.Generator().manual_seed(5)
+    vol = torch.randn(1, slices, 512, 512, generator=g).to(dev)
+    pred.predict_logits(vol[:, :2 * tile_batch * world])   # warm-up (allocator, cuDNN algorithm choice)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = pred.predict_logits(vol)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = max_over_ranks(e0.elapsed_time(e1), dev, world)
+    return {"volumes_per_s": 1e3 / ms, "slices_per_s": slices * 1e3 / ms, "seconds_per_volume": ms / 1e3,
+            "volume": [1, slices, 512, 512], "tile_batch": tile_batch, "forwards_per_rank": pred.forwards,
+            "mirroring": "axes (0, 1), 4 passes per tile stacked into one forward", "autocast": "fp16",
+            "scaling": "strong", "finite": bool(torch.isfinite(out).all()),
+            "merge": "all_reduce(sum) of fp16 logits + weights over NCCL, then divide" if world > 1 else "single rank"}
+
+
 def run_gpu_arm(args):
     import torch
     import torch.distributed as dist
@@ -460,6 +493,13 @@ def run_gpu_arm(args):
             train = train_run(dev, world, args.train_steps, 2, args.train_batch)
         except Exception as ex:  # report, never fake
             train = {"patches_per_s": None, "error": repr(ex)[:300]}
+    infer = None
+    if not args.no_infer:
+        torch.cuda.empty_cache()
+        try:
+            infer = infer_run(dev, world, args.infer_slices, args.infer_tile_batch)
+        except Exception as ex:  # report, never fake
+            infer = {"volumes_per_s": None, "error": repr(ex)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu:
         r = cpu_sample_run(1, 1)
         cpu = {"value": r["gbps"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
@@ -478,7 +518,7 @@ def run_gpu_arm(args):
                                    "128 steps; all 80 launches per step; algorithmic bytes 4*(5E+4S) per launch, "
                                    "achieved = sum of bytes / sum of CUDA-event durations of those launches)",
                          "share_of_step": bwd_ms / (ms_per_step * args.steps)},
-            "train": train, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "train": train, "infer": infer, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
@@ -495,6 +535,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-infer", action="store_true")
+    ap.add_argument("--infer-slices", type=int, default=200)
+    ap.add_argument("--infer-tile-batch", type=int, default=4)
     ap.add_argument("--train-steps", type=int, default=3)
     ap.add_argument("--train-batch", type=int, default=BATCH, help="per-GPU batch of the M2Net training leg")
     args = ap.parse_args()

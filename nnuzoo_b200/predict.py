@@ -1,0 +1,185 @@
+"""Sliding-window inference with the tiles sharded over GPUs and a gaussian-weighted logit merge
+(BASELINE config 5).
+
+Mirror of the reference predictor's inner path:
+  compute_gaussian / compute_steps_for_sliding_window   nnunetv2/inference/sliding_window_prediction.py:11-56
+  slicers (2-D tiles walked slice by slice through a volume, or same-dimensional tiles)
+                                                         nnunetv2/inference/predict_from_raw_data.py:515-547
+  mirror-and-predict test-time augmentation              :549-565
+  fp16 accumulators, ``logits += prediction * gaussian``, ``n += gaussian``, final division, inf check
+                                                         :567-634
+What is different, by design:
+  * ``tile_batch`` tiles go through the network per forward (the reference uses batch 1, :614), and the mirrored
+    copies of a batch are stacked into the same forward when ``stack_mirrors`` -- an eval-mode network treats samples
+    independently, so the per-tile results are the same numbers;
+  * the tile list is sharded ``slicers[rank::world]`` over the ranks of the default process group; every rank
+    accumulates its own tiles and the two accumulators are summed with ONE all-reduce each (NCCL over NVLink)
+    *before* the division -- exact for disjoint tiles (2-D slices of a volume), fp16 summation-order tolerance
+    for overlapping ones.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def _gauss_1d(n: int, sigma: float, truncate: float = 4.0) -> torch.Tensor:
+    """Response of scipy.ndimage.gaussian_filter (mode constant) to a unit impulse at n // 2, one axis, fp64."""
+    radius = int(truncate * sigma + 0.5)
+    x = torch.arange(-radius, radius + 1, dtype=torch.float64)
+    w = torch.exp(-0.5 * (x / sigma) ** 2)
+    w = w / w.sum()
+    out = torch.zeros(n, dtype=torch.float64)
+    c = n // 2
+    lo, hi = max(0, c - radius), min(n, c + radius + 1)
+    out[lo:hi] = w[lo - (c - radius):hi - (c - radius)]
+    return out
+
+
+def compute_gaussian(tile_size: Sequence[int], sigma_scale: float = 1.0 / 8, value_scaling_factor: float = 1.0,
+                     dtype=torch.float16, device="cpu") -> torch.Tensor:
+    """Importance map of one tile (sliding_window_prediction.py:11-29): a gaussian centred on the tile, sigma =
+    size * sigma_scale per axis, scaled to max = value_scaling_factor, zeros replaced by the smallest non-zero."""
+    g = None
+    for n in tile_size:
+        a = _gauss_1d(int(n), n * sigma_scale)
+        g = a if g is None else g.unsqueeze(-1) * a
+    g = (g / g.max() * value_scaling_factor).to(dtype)
+    nz = g != 0
+    if not bool(nz.all()):
+        g[~nz] = g[nz].min()
+    return g.to(device)
+
+
+def compute_steps_for_sliding_window(image_size: Sequence[int], tile_size: Sequence[int],
+                                     tile_step_size: float) -> List[List[int]]:
+    """Tile origins per axis: at most tile * step apart, evenly spread, last tile flush with the border
+    (sliding_window_prediction.py:32-56)."""
+    if not 0 < tile_step_size <= 1:
+        raise ValueError("step_size must be larger than 0 and smaller or equal to 1")
+    steps = []
+    for size, tile in zip(image_size, tile_size):
+        if size < tile:
+            raise ValueError("image size must be as large or larger than patch_size")
+        n = int(math.ceil((size - tile) / (tile * tile_step_size))) + 1
+        span = size - tile
+        stride = span / (n - 1) if n > 1 else 0.0
+        steps.append([int(round(stride * i)) for i in range(n)])
+    return steps
+
+
+def sliding_window_slicers(image_size: Sequence[int], patch_size: Sequence[int], tile_step_size: float):
+    """Tuples indexing a (c, *image_size) array, in the reference's order (predict_from_raw_data.py:515-547):
+    with a patch one dimension short of the image, every index of the first axis is tiled in 2-D."""
+    image_size, patch_size = tuple(image_size), tuple(patch_size)
+    slicers = []
+    if len(patch_size) < len(image_size):
+        if len(patch_size) != len(image_size) - 1:
+            raise ValueError("patch_size may be at most one dimension shorter than the image")
+        steps = compute_steps_for_sliding_window(image_size[1:], patch_size, tile_step_size)
+        for d in range(image_size[0]):
+            for origin in itertools.product(*steps):
+                slicers.append((slice(None), d, *[slice(o, o + t) for o, t in zip(origin, patch_size)]))
+    else:
+        steps = compute_steps_for_sliding_window(image_size, patch_size, tile_step_size)
+        for origin in itertools.product(*steps):
+            slicers.append((slice(None), *[slice(o, o + t) for o, t in zip(origin, patch_size)]))
+    return slicers
+
+
+def pad_to_patch(image: torch.Tensor, patch_size: Sequence[int]):
+    """Centre zero-padding of the trailing axes up to the patch size (acvl_utils pad_nd_image as called at
+    predict_from_raw_data.py:668-670); returns the padded image and the slicer that undoes it."""
+    nd = len(patch_size)
+    shape = image.shape[-nd:]
+    pads, revert = [], [slice(None)] * (image.dim() - nd)
+    for s, p in zip(shape, patch_size):
+        total = max(p - s, 0)
+        lo = total // 2
+        pads.append((lo, total - lo))
+        revert.append(slice(lo, lo + s))
+    if any(a or b for a, b in pads):
+        flat = [v for ab in reversed(pads) for v in ab]
+        image = torch.nn.functional.pad(image, flat, mode="constant", value=0)
+    return image, tuple(revert)
+
+
+class SlidingWindowPredictor:
+    """``predict_logits((c, *spatial)) -> (heads, *spatial)`` fp16, the reference's
+    predict_sliding_window_return_logits (predict_from_raw_data.py:646-690) for one set of weights."""
+
+    def __init__(self, network: torch.nn.Module, patch_size: Sequence[int], num_heads: int, device,
+                 tile_step_size: float = 0.5, use_gaussian: bool = True, use_mirroring: bool = True,
+                 mirror_axes: Sequence[int] | None = None, tile_batch: int = 4, stack_mirrors: bool = True,
+                 autocast_dtype=torch.float16, results_dtype=torch.float16):
+        self.device = torch.device(device)
+        self.network = network.to(self.device).eval()
+        self.patch_size = tuple(int(p) for p in patch_size)
+        self.num_heads = num_heads
+        self.tile_step_size = tile_step_size
+        self.use_gaussian = use_gaussian
+        axes = tuple(range(len(self.patch_size))) if mirror_axes is None else tuple(mirror_axes)
+        self.mirror_axes = axes if use_mirroring else ()
+        self.tile_batch = max(1, int(tile_batch))
+        self.stack_mirrors = stack_mirrors
+        self.autocast_dtype = autocast_dtype
+        self.results_dtype = results_dtype
+        self.forwards = 0   # network invocations of the last call (for the bench)
+
+    # -- test-time augmentation (predict_from_raw_data.py:549-565) on a batch of tiles ------------------------------
+    def _mirror_and_predict(self, x: torch.Tensor) -> torch.Tensor:
+        combos = [c for i in range(len(self.mirror_axes))
+                  for c in itertools.combinations([m + 2 for m in self.mirror_axes], i + 1)]
+        if not combos:
+            self.forwards += 1
+            return self.network(x)
+        if self.stack_mirrors:
+            n = x.shape[0]
+            out = self.network(torch.cat([x] + [torch.flip(x, c) for c in combos], 0))
+            self.forwards += 1
+            pred = out[:n].clone()
+            for i, c in enumerate(combos, start=1):
+                pred += torch.flip(out[i * n:(i + 1) * n], c)
+        else:
+            pred = self.network(x)
+            for c in combos:
+                pred += torch.flip(self.network(torch.flip(x, c)), c)
+            self.forwards += 1 + len(combos)
+        pred /= (len(combos) + 1)
+        return pred
+
+    @torch.no_grad()
+    def predict_logits(self, image: torch.Tensor) -> torch.Tensor:
+        dev = self.device
+        ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        rank, world = (dist.get_rank(), dist.get_world_size()) if ddp else (0, 1)
+        self.forwards = 0
+        data, revert = pad_to_patch(image, self.patch_size)
+        data = data.to(dev)
+        slicers = sliding_window_slicers(data.shape[1:], self.patch_size, self.tile_step_size)
+        mine = slicers[rank::world]
+        logits = torch.zeros((self.num_heads, *data.shape[1:]), dtype=self.results_dtype, device=dev)
+        n_pred = torch.zeros(data.shape[1:], dtype=self.results_dtype, device=dev)
+        gaussian = (compute_gaussian(self.patch_size, 1.0 / 8, 10, self.results_dtype, dev) if self.use_gaussian
+                    else torch.ones(self.patch_size, dtype=self.results_dtype, device=dev))
+        with torch.autocast(dev.type, dtype=self.autocast_dtype, enabled=dev.type == "cuda"):
+            for i in range(0, len(mine), self.tile_batch):
+                group = mine[i:i + self.tile_batch]
+                batch = torch.stack([data[sl] for sl in group], 0)
+                pred = self._mirror_and_predict(batch).to(self.results_dtype)
+                if self.use_gaussian:
+                    pred *= gaussian
+                for sl, p in zip(group, pred):
+                    logits[sl] += p
+                    n_pred[sl[1:]] += gaussian
+        if ddp:  # the one exchange step of this path: sum the per-rank accumulators, then divide
+            dist.all_reduce(logits, op=dist.ReduceOp.SUM)
+            dist.all_reduce(n_pred, op=dist.ReduceOp.SUM)
+        logits /= n_pred
+        if bool(torch.isinf(logits).any()):
+            raise RuntimeError("Encountered inf in predicted array: reduce value_scaling_factor or use fp32 results")
+        return logits[(slice(None), *revert[1:])]

@@ -113,3 +113,21 @@ def test_m2net_gpu_bf16_autocast_train_step_runs():
     loss.backward()
     assert torch.isfinite(loss)
     assert all(torch.isfinite(p.grad).all() for p in net.parameters() if p.grad is not None)
+
+
+@pytest.mark.gpu
+def test_sliding_window_on_m2net_batched_tiles_equal_one_by_one():
+    """Config 5 in miniature: 2-D tiles through a (1, 3, 96, 64) volume; tile_batch 4 with stacked mirrors must give
+    the logits of the reference's one-tile-at-a-time loop (fp16 autocast: tolerance of the fp16 accumulators)."""
+    from nnuzoo_b200.m2net import get_m2net
+    from nnuzoo_b200.predict import SlidingWindowPredictor
+    torch.manual_seed(1)
+    net = get_m2net(1, 4, False).cuda().eval()
+    vol = torch.randn(1, 3, 96, 64)
+    a = SlidingWindowPredictor(net, (64, 64), 4, "cuda", tile_batch=1, stack_mirrors=False).predict_logits(vol)
+    b = SlidingWindowPredictor(net, (64, 64), 4, "cuda", tile_batch=4, stack_mirrors=True).predict_logits(vol)
+    assert a.shape == (4, 3, 96, 64) and a.dtype == torch.float16
+    assert bool(torch.isfinite(a).all())
+    scale = float(a.float().abs().max())
+    assert float((a.float() - b.float()).abs().max()) <= 2e-2 * scale
+    assert (a.argmax(0) == b.argmax(0)).float().mean() > 0.98
