@@ -183,6 +183,22 @@ int nz_proj_wgrad(const void* G, const void* X, float* dW, int32_t g_dtype, int3
                   int32_t M, int32_t N, int64_t L, const int64_t* g_stride, const int64_t* x_stride, void* stream);
 
 /*
+ * Channels-last LayerNorm over the last axis of a contiguous (rows, C) array -- ln_1 / out_norm of every VSS block
+ * (m2net.py:524, :220) and the norms of patch merge / expand (:241, :286-290); the reference calls nn.LayerNorm.
+ * x / dx have element type in_dtype, y / dy out_dtype (equal, or one of the two fp32: under autocast the reference
+ * normalises in fp32 and the consumer casts); gamma / beta (may be NULL) and the saved statistics mean / rstd (rows
+ * each) are fp32; biased variance, y = (x - mean) * rstd * gamma + beta.  dgamma / dbeta (C each, may be NULL) are
+ * ACCUMULATED INTO.  Supported: C / E a power of two, C <= 32 * 32 with E = 4 (fp32 involved) or 8 elements;
+ * nz_layernorm_supported tells (M2Net: C = 16 .. 1024).
+ */
+int nz_layernorm_supported(int32_t C, int32_t in_dtype, int32_t out_dtype);
+int nz_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int64_t rows, int32_t C, int32_t in_dtype, int32_t out_dtype, float eps, void* stream);
+int nz_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                     float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t in_dtype, int32_t out_dtype,
+                     void* stream);
+
+/*
  * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):
  * every pointer in `desc` is a HOST pointer, strides as above; the call stages host -> device,
  * runs nz_scan_fwd (and nz_scan_bwd when desc->dout != NULL) and copies the results back,

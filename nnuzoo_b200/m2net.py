@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .norm import LayerNorm
 from .ss2d import SS2D
 
 __all__ = ["M2Net", "MU", "get_m2net"]
@@ -76,13 +77,14 @@ class REBNCONV(nn.Module):
 class PatchMerging2D(nn.Module):
     """Space-to-depth, LayerNorm, Linear (m2net.py:228-273)."""
 
-    def __init__(self, input_dim, scale, output_features=None, norm_layer=nn.LayerNorm):
+    def __init__(self, input_dim, scale, output_features=None, norm_layer=LayerNorm):
         super().__init__()
         self.scale = scale
         self.input_feature_size = scale * scale * input_dim
         self.output_features = output_features or input_dim * scale
         self.reduction = nn.Linear(self.input_feature_size, self.output_features, bias=False)
         self.norm = norm_layer(self.input_feature_size)
+        self.norm.feeds_linear = True      # only consumer: self.reduction
 
     def forward(self, x, permute=False):
         if permute:
@@ -101,7 +103,7 @@ class PatchExpand(nn.Module):
     """Depth-to-space up-sampling (m2net.py:276-319); takes (B, C, H, W), returns channels-last unless
     ``permute``. With ``output_dim`` the shuffle comes first, then Linear(dim / scale^2 -> output_dim)."""
 
-    def __init__(self, dim, scale, output_dim=None, norm_layer=nn.LayerNorm):
+    def __init__(self, dim, scale, output_dim=None, norm_layer=LayerNorm):
         super().__init__()
         self.dim, self.scale, self.output_dim = dim, scale, output_dim
         if output_dim is None:
@@ -123,9 +125,10 @@ class PatchExpand(nn.Module):
 class VSSBlock(nn.Module):
     """x + DropPath(SS2D(LayerNorm(x)))  (m2net.py:513-530)."""
 
-    def __init__(self, hidden_dim, drop_path=0.0, norm_layer=nn.LayerNorm, attn_drop_rate=0.0, d_state=16, **kw):
+    def __init__(self, hidden_dim, drop_path=0.0, norm_layer=LayerNorm, attn_drop_rate=0.0, d_state=16, **kw):
         super().__init__()
         self.ln_1 = norm_layer(hidden_dim)
+        self.ln_1.feeds_linear = True      # only consumer: SS2D.in_proj
         self.self_attention = SS2D(d_model=hidden_dim, dropout=attn_drop_rate, d_state=d_state, **kw)
         self.drop_path = DropPath(drop_path)
 
@@ -136,7 +139,7 @@ class VSSBlock(nn.Module):
 class VSSLayer(nn.Module):
     """``depth`` VSSBlocks (+ optional downsample), m2net.py:533-595."""
 
-    def __init__(self, dim, depth, attn_drop=0.0, drop_path=0.0, norm_layer=nn.LayerNorm, downsample=None,
+    def __init__(self, dim, depth, attn_drop=0.0, drop_path=0.0, norm_layer=LayerNorm, downsample=None,
                  use_checkpoint=False, d_state=16):
         super().__init__()
         self.dim = dim
@@ -179,7 +182,7 @@ class VSSMEncoder(nn.Module):
     """m2net.py:598-710. Returns [stem output or None, stage outputs (B, C, H, W) ...]."""
 
     def __init__(self, patch_size=4, in_chans=3, depths=(2, 2, 9, 2), dims=(96, 192, 384, 768), d_state=16,
-                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=nn.LayerNorm, patch_norm=True,
+                 drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.1, norm_layer=LayerNorm, patch_norm=True,
                  use_checkpoint=False, skip_first_downsample=False, skip_last_downsample=False, add_last=False,
                  out_ch=None):
         super().__init__()
@@ -238,7 +241,7 @@ class VSSMDecoder(nn.Module):
         for s in range(1, n):
             below, skip_ch = f[-s], f[-(s + 1)]
             expands.append(None if (s == 1 and skip_first_expand) else PatchExpand(below, 2, below))
-            stages.append(VSSLayer(skip_ch, 1, 0.0, rates[sum(depths[:s - 1]):sum(depths[:s])], nn.LayerNorm, None,
+            stages.append(VSSLayer(skip_ch, 1, 0.0, rates[sum(depths[:s - 1]):sum(depths[:s])], LayerNorm, None,
                                    False, d_state if d_state is not None else -(-2 * skip_ch // 6)))
             segs.append(nn.Conv2d(skip_ch, num_classes, 1, 1, 0, bias=True))
             backs.append(nn.Linear(2 * skip_ch, skip_ch))

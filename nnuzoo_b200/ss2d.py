@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .cross_scan import cross_merge, cross_scan
+from .norm import LayerNorm
 from .proj import grouped_proj
 from .selective_scan_interface import selective_scan_fn
 
@@ -61,7 +62,7 @@ class _CrossScanSSM(nn.Module):
         self.A_logs = self.A_log_init(d_state, self.d_inner, copies=k, merge=True)  # (K * d_inner, N)
         self.Ds = self.D_init(self.d_inner, copies=k, merge=True)                   # (K * d_inner)
         self.selective_scan = selective_scan_fn
-        self.out_norm = nn.LayerNorm(self.d_inner)
+        self.out_norm = LayerNorm(self.d_inner)
         self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias, **factory_kwargs)
         self.dropout = nn.Dropout(dropout) if dropout > 0.0 else None
 

@@ -118,14 +118,16 @@ def test_m2net_gpu_bf16_autocast_train_step_runs():
 @pytest.mark.gpu
 def test_sliding_window_on_m2net_batched_tiles_equal_one_by_one():
     """Config 5 in miniature: 2-D tiles through a (1, 3, 96, 64) volume; tile_batch 4 with stacked mirrors must give
-    the logits of the reference's one-tile-at-a-time loop (fp16 autocast: tolerance of the fp16 accumulators)."""
+    the logits of the reference's one-tile-at-a-time loop (tolerance of bf16 autocast and the fp16 accumulators)."""
     from nnuzoo_b200.m2net import get_m2net
     from nnuzoo_b200.predict import SlidingWindowPredictor
     torch.manual_seed(1)
     net = get_m2net(1, 4, False).cuda().eval()
     vol = torch.randn(1, 3, 96, 64)
-    a = SlidingWindowPredictor(net, (64, 64), 4, "cuda", tile_batch=1, stack_mirrors=False).predict_logits(vol)
-    b = SlidingWindowPredictor(net, (64, 64), 4, "cuda", tile_batch=4, stack_mirrors=True).predict_logits(vol)
+    # bf16 autocast: a randomly initialised net with eval-mode BatchNorm overflows fp16 (the reference's default)
+    kw = dict(autocast_dtype=torch.bfloat16)
+    a = SlidingWindowPredictor(net, (64, 64), 4, "cuda", tile_batch=1, stack_mirrors=False, **kw).predict_logits(vol)
+    b = SlidingWindowPredictor(net, (64, 64), 4, "cuda", tile_batch=4, stack_mirrors=True, **kw).predict_logits(vol)
     assert a.shape == (4, 3, 96, 64) and a.dtype == torch.float16
     assert bool(torch.isfinite(a).all())
     scale = float(a.float().abs().max())
