@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/nnuzoo_b200.h"
 
@@ -122,6 +123,147 @@ __global__ void __launch_bounds__(kProjThreads) proj_wgrad_kernel(ProjWgradArgs 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// bf16 x bf16 path: the same reduction on the tensor cores (mma.sync m16n8k16, fp32 accumulate).  The op stays
+// HBM-bound -- per 64 positions a CTA moves (M + N) * 128 bytes and issues MT * NT * 4 MMAs -- so the kernel is a
+// copy pipeline: 16-byte cp.async of whole bf16 row segments into a 3-stage ring (rows XOR-swizzled by 16-byte chunk
+// so ldmatrix is conflict-free), ldmatrix + mma on the oldest stage.  MMA tiles are dealt round-robin to the warps.
+constexpr int kTcStages = 3;
+constexpr int kTcRowB = kProjTL * 2;  // bytes of one staged row (64 bf16)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int TPW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) proj_wgrad_tc_kernel(ProjWgradArgs a, int MT, int NT) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int Mp = MT * 16, Np = NT * 8, rows = Mp + Np;
+  const int stageB = rows * kTcRowB;
+  const int bk = blockIdx.y, b = bk / a.K, k = bk % a.K;
+  const __nv_bfloat16* G = static_cast<const __nv_bfloat16*>(a.G) + b * a.gs_b + k * a.gs_k;
+  const __nv_bfloat16* X = static_cast<const __nv_bfloat16*>(a.X) + b * a.xs_b + k * a.xs_k;
+  // padding rows are never written by the copies: zero the whole ring once
+  for (int i = t; i < kTcStages * stageB / 16; i += WARPS * 32) reinterpret_cast<uint4*>(smraw)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
+  const long ntiles = a.L / kProjTL;
+  const long tile0 = blockIdx.x * a.tiles_per_chunk;
+  long tile1 = tile0 + a.tiles_per_chunk;
+  if (tile1 > ntiles) tile1 = ntiles;
+  const int nt_local = (int)(tile1 - tile0);
+
+  auto issue = [&](int it) {  // stage tile `it` of this CTA into ring slot it % kTcStages
+    if (it < nt_local) {
+      unsigned char* st = smraw + (it % kTcStages) * stageB;
+      const long l0 = (tile0 + it) * kProjTL;
+      for (int i = t; i < (a.M + a.N) * 8; i += WARPS * 32) {
+        const int r = i >> 3, c = i & 7;
+        const bool isg = r < a.M;
+        const int srow = isg ? r : Mp + (r - a.M);
+        const __nv_bfloat16* src = isg ? G + r * a.gs_m + l0 + c * 8 : X + (r - a.M) * a.xs_n + l0 + c * 8;
+        const uint32_t dst = smem_u32(st + srow * kTcRowB + ((c ^ (srow & 7)) << 4));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+
+  float acc[TPW][4];
+#pragma unroll
+  for (int j = 0; j < TPW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const int ntile_mma = MT * NT;
+
+  issue(0);
+  issue(1);
+  for (int it = 0; it < nt_local; ++it) {
+    issue(it + 2);
+    asm volatile("cp.async.wait_group 2;");
+    __syncthreads();
+    const unsigned char* st = smraw + (it % kTcStages) * stageB;
+#pragma unroll
+    for (int j = 0; j < TPW; ++j) {
+      const int tid = warp + j * WARPS;
+      if (tid < ntile_mma) {
+        const int mt = tid % MT, nt = tid / MT;
+        const int arow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int brow = Mp + nt * 8 + (lane & 7);
+#pragma unroll
+        for (int ks = 0; ks < kProjTL / 16; ++ks) {
+          uint32_t a0, a1, a2, a3, b0, b1;
+          const int ac = ks * 2 + (lane >> 4);
+          const int bc = ks * 2 + ((lane >> 3) & 1);
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                       : "r"(smem_u32(st + arow * kTcRowB + ((ac ^ (arow & 7)) << 4))));
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                       : "=r"(b0), "=r"(b1)
+                       : "r"(smem_u32(st + brow * kTcRowB + ((bc ^ (brow & 7)) << 4))));
+          asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+                       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+        }
+      }
+    }
+    __syncthreads();  // the slot is refilled by the next iteration's issue()
+  }
+  asm volatile("cp.async.wait_group 0;");
+  float* out = a.dW + (long)k * a.M * a.N;
+#pragma unroll
+  for (int j = 0; j < TPW; ++j) {
+    const int tid = warp + j * WARPS;
+    if (tid < ntile_mma) {
+      const int mt = tid % MT, nt = tid / MT;
+      const int m0 = mt * 16 + (lane >> 2), n0 = nt * 8 + (lane & 3) * 2;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int m = m0 + (q >> 1) * 8, n = n0 + (q & 1);
+        if (m < a.M && n < a.N) atomicAdd(out + m * a.N + n, acc[j][q]);
+      }
+    }
+  }
+}
+
+static bool tc_eligible(const ProjWgradArgs& a) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return a.L % kProjTL == 0 && al(a.G) && al(a.X) && a.gs_b % 8 == 0 && a.gs_k % 8 == 0 && a.gs_m % 8 == 0 &&
+         a.xs_b % 8 == 0 && a.xs_k % 8 == 0 && a.xs_n % 8 == 0;
+}
+
+static int launch_wgrad_tc(const ProjWgradArgs& a, cudaStream_t st) {
+  const int MT = (a.M + 15) / 16, NT = (a.N + 7) / 8;
+  const int tiles = MT * NT;
+  const size_t smem = (size_t)kTcStages * (MT * 16 + NT * 8) * kTcRowB;
+  dim3 grid(a.chunks, a.B * a.K);
+#define NZ_TC_LAUNCH(TPW, WARPS)                                                                                  \
+  do {                                                                                                            \
+    auto kern = proj_wgrad_tc_kernel<TPW, WARPS>;                                                                 \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {      \
+      set_error("proj_wgrad_tc: cannot reserve %zu bytes of shared memory", smem);                                \
+      return NZ_ECUDA;                                                                                            \
+    }                                                                                                             \
+    kern<<<grid, WARPS * 32, smem, st>>>(a, MT, NT);                                                              \
+  } while (0)
+  if (tiles <= 4)
+    NZ_TC_LAUNCH(1, 4);
+  else if (tiles <= 12)
+    NZ_TC_LAUNCH(3, 4);
+  else if (tiles <= 24)
+    NZ_TC_LAUNCH(3, 8);
+  else if (tiles <= 48)
+    NZ_TC_LAUNCH(6, 8);
+  else if (tiles <= 96)
+    NZ_TC_LAUNCH(12, 8);
+  else
+    return NZ_EUNSUPPORTED;
+#undef NZ_TC_LAUNCH
+  count_launch(1);
+  if (cudaGetLastError() != cudaSuccess) {
+    set_error("proj_wgrad_tc launch failed");
+    return NZ_ECUDA;
+  }
+  return NZ_OK;
+}
+
 template <typename TG, typename TX>
 static int launch_wgrad(const ProjWgradArgs& a, cudaStream_t st) {
   const size_t smem = (size_t)(a.M + a.N) * kProjTLP * sizeof(float);
@@ -179,6 +321,10 @@ extern "C" int nz_proj_wgrad(const void* G, const void* X, float* dW, int32_t g_
   a.tiles_per_chunk = (ntiles + want - 1) / want;
   a.chunks = (int)((ntiles + a.tiles_per_chunk - 1) / a.tiles_per_chunk);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g_dtype == NZ_BF16 && x_dtype == NZ_BF16 && tc_eligible(a) && !getenv("NZ_PROJ_NO_TC")) {
+    const int rc = launch_wgrad_tc(a, st);
+    if (rc != NZ_EUNSUPPORTED) return rc;
+  }
 #define NZ_DISPATCH_X(TG)                                                    \
   switch (x_dtype) {                                                         \
     case NZ_F32: return launch_wgrad<TG, float>(a, st);                      \
