@@ -138,6 +138,106 @@ __global__ void cross_merge_bwd_kernel(const float* __restrict__ dy, float* __re
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-D fast path: the same maps, tiled.  A CTA owns a 32 x 32 (h, w) tile of one (batch, channel) plane and moves it
+// through shared memory, so both the row-major walks (k0, k2: contiguous in w) and the column-major walks (k1, k3:
+// contiguous in h) touch whole 128-byte lines; the one-thread-per-element kernels above read the transposed
+// directions with a stride of H or W elements (one useful element per 32-byte sector).  Same values, same fp32
+// association order, so still bit-identical to the reference expressions.
+constexpr int kCT = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(256) cross_scan2d_tiled_kernel(const T* __restrict__ x, T* __restrict__ xs, long planes,
+                                                                 int dim, long H, long W, int tiles_w, int tiles_h) {
+  __shared__ T tile[kCT][kCT + 1];
+  const long L = H * W;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (long blk = blockIdx.x;; blk += gridDim.x) {
+    const long plane = blk / ((long)tiles_w * tiles_h);
+    const int tr = (int)(blk % ((long)tiles_w * tiles_h));
+    if (plane >= planes) break;
+    const long h0 = (long)(tr / tiles_w) * kCT, w0 = (long)(tr % tiles_w) * kCT;
+    const long b = plane / dim;
+    const int dd = (int)(plane % dim);
+    const T* src = x + plane * L;
+    T* o0 = xs + ((b * 4 + 0) * dim + dd) * L;
+    T* o1 = xs + ((b * 4 + 1) * dim + dd) * L;
+    T* o2 = xs + ((b * 4 + 2) * dim + dd) * L;
+    T* o3 = xs + ((b * 4 + 3) * dim + dd) * L;
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {
+      const long h = h0 + ty + r, w = w0 + tx;
+      if (h < H && w < W) {
+        const T v = src[h * W + w];
+        tile[ty + r][tx] = v;
+        o0[h * W + w] = v;
+        o2[L - 1 - (h * W + w)] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {
+      const long w = w0 + ty + r, h = h0 + tx;
+      if (h < H && w < W) {
+        const T v = tile[tx][ty + r];
+        o1[w * H + h] = v;
+        o3[L - 1 - (w * H + h)] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// out_y (b, 4, d, L) -> y (b, d, L): ((y0[p] + y2[L-1-p]) + y1[t(p)]) + y3[L-1-t(p)], t(p) = w * H + h
+__global__ void __launch_bounds__(256) cross_merge2d_tiled_kernel(const float* __restrict__ oy, float* __restrict__ y,
+                                                                  long planes, int dim, long H, long W, int tiles_w,
+                                                                  int tiles_h) {
+  __shared__ float t1[kCT][kCT + 1], t3[kCT][kCT + 1];
+  const long L = H * W;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long blk = blockIdx.x;; blk += gridDim.x) {
+    const long plane = blk / ((long)tiles_w * tiles_h);
+    const int tr = (int)(blk % ((long)tiles_w * tiles_h));
+    if (plane >= planes) break;
+    const long h0 = (long)(tr / tiles_w) * kCT, w0 = (long)(tr % tiles_w) * kCT;
+    const long b = plane / dim;
+    const int dd = (int)(plane % dim);
+    const float* i0 = oy + ((b * 4 + 0) * dim + dd) * L;
+    const float* i1 = oy + ((b * 4 + 1) * dim + dd) * L;
+    const float* i2 = oy + ((b * 4 + 2) * dim + dd) * L;
+    const float* i3 = oy + ((b * 4 + 3) * dim + dd) * L;
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {  // column-major directions: contiguous in h
+      const long w = w0 + ty + r, h = h0 + tx;
+      if (h < H && w < W) {
+        t1[ty + r][tx] = i1[w * H + h];
+        t3[ty + r][tx] = i3[L - 1 - (w * H + h)];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {
+      const long h = h0 + ty + r, w = w0 + tx;
+      if (h < H && w < W) {
+        const long p = h * W + w;
+        float acc = i0[p];
+        acc = acc + i2[L - 1 - p];
+        acc = acc + t1[tx][ty + r];
+        acc = acc + t3[tx][ty + r];
+        y[plane * L + p] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+static int tiled_grid(long planes, long H, long W, int* tw, int* th) {
+  *tw = (int)((W + kCT - 1) / kCT), *th = (int)((H + kCT - 1) / kCT);
+  const long blocks = planes * *tw * *th, cap = 148L * 32;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
 static int launch_cfg(long total, int* grid) {
   const int threads = 256;
   long blocks = (total + threads - 1) / threads;
@@ -171,6 +271,18 @@ int nz_cross_scan(const void* x, void* xs, int32_t dtype, int32_t batch, int32_t
   int grid;
   const int threads = nz::launch_cfg(rows * 2 * nspatial * s.L, &grid);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (nspatial == 2 && (dtype == NZ_F32 || dtype == NZ_BF16 || dtype == NZ_F16)) {
+    int tw, th;
+    const int g = nz::tiled_grid(rows, s.H, s.W, &tw, &th);
+    if (dtype == NZ_F32)
+      nz::cross_scan2d_tiled_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(x),
+                                                                 static_cast<uint32_t*>(xs), rows, dim, s.H, s.W, tw, th);
+    else
+      nz::cross_scan2d_tiled_kernel<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(x),
+                                                                 static_cast<uint16_t*>(xs), rows, dim, s.H, s.W, tw, th);
+    nz::count_launch(1);
+    return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+  }
   if (dtype == NZ_F32)
     nz::cross_scan_kernel<uint32_t><<<grid, threads, 0, st>>>(static_cast<const uint32_t*>(x),
                                                               static_cast<uint32_t*>(xs), rows, dim, s);
@@ -188,6 +300,14 @@ int nz_cross_merge(const float* out_y, float* y, int32_t batch, int32_t dim, int
   nz::Dims s;
   if (!out_y || !y || batch < 1 || dim < 1 || !nz::make_dims(nspatial, spatial, &s)) return NZ_EINVAL;
   const long rows = (long)batch * dim;
+  if (nspatial == 2) {
+    int tw, th;
+    const int g = nz::tiled_grid(rows, s.H, s.W, &tw, &th);
+    nz::cross_merge2d_tiled_kernel<<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out_y, y, rows, dim, s.H, s.W,
+                                                                                         tw, th);
+    nz::count_launch(1);
+    return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+  }
   int grid;
   const int threads = nz::launch_cfg(rows * s.L, &grid);
   nz::cross_merge_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out_y, y, rows, dim, s, mode);
@@ -200,6 +320,14 @@ int nz_cross_merge_bwd(const float* dy, float* d_out_y, int32_t batch, int32_t d
   nz::Dims s;
   if (!dy || !d_out_y || batch < 1 || dim < 1 || !nz::make_dims(nspatial, spatial, &s)) return NZ_EINVAL;
   const long rows = (long)batch * dim;
+  if (nspatial == 2) {  // in 2-D the adjoint of the merge is the scan permutation applied to dy (fp32)
+    int tw, th;
+    const int g = nz::tiled_grid(rows, s.H, s.W, &tw, &th);
+    nz::cross_scan2d_tiled_kernel<uint32_t><<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint32_t*>(dy), reinterpret_cast<uint32_t*>(d_out_y), rows, dim, s.H, s.W, tw, th);
+    nz::count_launch(1);
+    return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+  }
   int grid;
   const int threads = nz::launch_cfg(rows * 2 * nspatial * s.L, &grid);
   nz::cross_merge_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, d_out_y, rows, dim, s,
