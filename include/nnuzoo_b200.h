@@ -199,6 +199,19 @@ int nz_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
                      void* stream);
 
 /*
+ * SS2D's depthwise 3x3 convolution (padding 1, stride 1) fused with its SiLU -- `self.act(self.conv2d(x))`,
+ * m2net.py:69-77 and :214-215; the reference calls nn.Conv2d(groups = d_inner) + nn.SiLU.  x, y, dy, dx: contiguous
+ * (batch, dim, H, W) of `dtype`; weight (dim, 1, 3, 3) and bias (dim, may be NULL) fp32; silu = 0 gives the plain
+ * convolution.  The backward recomputes the pre-activation; dweight (dim, 3, 3) / dbias (dim), either may be NULL, are
+ * ACCUMULATED INTO.
+ */
+int nz_dwconv3x3_fwd(const void* x, const float* weight, const float* bias, void* y, int32_t dtype, int32_t batch,
+                     int32_t dim, int32_t H, int32_t W, int32_t silu, void* stream);
+int nz_dwconv3x3_bwd(const void* x, const void* dy, const float* weight, const float* bias, void* dx, float* dweight,
+                     float* dbias, int32_t dtype, int32_t batch, int32_t dim, int32_t H, int32_t W, int32_t silu,
+                     void* stream);
+
+/*
  * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):
  * every pointer in `desc` is a HOST pointer, strides as above; the call stages host -> device,
  * runs nz_scan_fwd (and nz_scan_bwd when desc->dout != NULL) and copies the results back,

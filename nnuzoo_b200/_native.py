@@ -103,6 +103,10 @@ def lib():
                 L.nz_layernorm_fwd.restype = ctypes.c_int
                 L.nz_layernorm_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
                 L.nz_layernorm_bwd.restype = ctypes.c_int
+                L.nz_dwconv3x3_fwd.argtypes = [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
+                L.nz_dwconv3x3_fwd.restype = ctypes.c_int
+                L.nz_dwconv3x3_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
+                L.nz_dwconv3x3_bwd.restype = ctypes.c_int
                 L.nz_sizeof_conv1d_desc.restype = _i64
                 if L.nz_sizeof_conv1d_desc() != ctypes.sizeof(NzConv1dDesc):
                     raise NativeLibraryError("NzConv1dDesc layout differs between _native.py and the .so")

@@ -10,6 +10,7 @@ Differences are confined to *how* forward_core executes:
     stack / flip / transpose-contiguous chains;
   * the scan is nnuzoo_b200.selective_scan_fn (no mamba_ssm dependency);
   * B/C are handed to the scan as the strided split views they are (no .contiguous());
+  * SS2D's depthwise 3x3 conv + SiLU is one kernel each way (nnuzoo_b200.dwconv);
   * the two projection einsums run as batched GEMMs whose weight gradient is our own reduction kernel
     (nnuzoo_b200.proj).
 """
@@ -22,6 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .cross_scan import cross_merge, cross_scan
+from .dwconv import dwconv3x3_silu
 from .norm import LayerNorm
 from .proj import grouped_proj
 from .selective_scan_interface import selective_scan_fn
@@ -157,7 +159,12 @@ class SS2D(_CrossScanSSM):
     def forward(self, x: torch.Tensor, **kwargs):
         bsz, H, W, _ = x.shape
         x, z = self.in_proj(x).chunk(2, dim=-1)                          # m2net.py:211-212
-        x = self.act(self.conv2d(x.permute(0, 3, 1, 2).contiguous()))    # :214-215
+        x = x.permute(0, 3, 1, 2).contiguous()
+        c = self.conv2d
+        if x.is_cuda and c.kernel_size == (3, 3) and c.padding == (1, 1) and c.dilation == (1, 1):
+            x = dwconv3x3_silu(x, c.weight, c.bias)                      # :214-215 as one kernel
+        else:
+            x = self.act(c(x))
         y = self.forward_core(x)
         return self._finish(y, z, bsz, (H, W))
 
