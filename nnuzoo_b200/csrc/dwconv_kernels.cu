@@ -7,7 +7,7 @@
 //
 // Forward: a thread owns one column and kRows consecutive rows of a plane and slides a 3x3 window down
 // (3 loads per new row, neighbours' loads hit L1).  Backward: a CTA owns a kTH x kTW tile; it first recomputes the
-// pre-activation on the tile plus a one-pixel ring and stores dpre = dy * silu'(pre) in shared memory, then every
+// pre-activation (from x staged in shared memory with a two-pixel ring) on the tile plus a one-pixel ring and stores dpre = dy * silu'(pre) in shared memory, then every
 // thread forms dx (the transposed stencil over dpre) and its share of dweight[3][3] / dbias, which are reduced over
 // the CTA (warp shuffles + shared memory) and flushed with 10 atomicAdds per CTA (caller zeroes them).
 #include <cuda_bf16.h>
@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_silu_bwd_kernel(const T* __rest
                                                                  const float* __restrict__ bias, T* __restrict__ dx,
                                                                  float* __restrict__ dwgt, float* __restrict__ dbias,
                                                                  long planes, int dim, int H, int W, int silu) {
+  __shared__ float xt[kTH + 4][kTW + 4];    // x on the tile + a two-pixel ring (zero outside the image)
   __shared__ float dpre[kTH + 2][kTW + 2];
   __shared__ float red[8][10];
   const int tiles_w = (W + kTW - 1) / kTW, tiles_h = (H + kTH - 1) / kTH;
@@ -117,9 +118,13 @@ __global__ void __launch_bounds__(256) dwconv3x3_silu_bwd_kernel(const T* __rest
     const float b = bias ? bias[d] : 0.f;
     const T* xp = x + plane * (long)H * W;
     const T* gp = dy + plane * (long)H * W;
-    auto xat = [&](int h, int w) -> float {
-      return (h >= 0 && h < H && w >= 0 && w < W) ? ld_f32<T>(xp + (long)h * W + w) : 0.f;
-    };
+    for (int i = t; i < (kTH + 4) * (kTW + 4); i += 256) {
+      const int rr = i / (kTW + 4), cc = i % (kTW + 4);
+      const int h = h0 + rr - 2, w = w0 + cc - 2;
+      xt[rr][cc] = (h >= 0 && h < H && w >= 0 && w < W) ? ld_f32<T>(xp + (long)h * W + w) : 0.f;
+    }
+    __syncthreads();
+    auto xat = [&](int h, int w) -> float { return xt[h - h0 + 2][w - w0 + 2]; };
     // phase 1: dpre on the tile + ring (zero outside the image: those outputs do not exist)
     for (int i = t; i < (kTH + 2) * (kTW + 2); i += 256) {
       const int rr = i / (kTW + 2), cc = i % (kTW + 2);
