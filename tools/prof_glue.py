@@ -3,7 +3,7 @@
 
     python tools/prof_glue.py            # prints one line per kernel / shape: ms, algorithmic GB/s, % of peak
 Algorithmic bytes: proj_wgrad reads G and X once ((M + N) * B*K*L elements); LayerNorm fwd reads x and writes y,
-bwd reads dy and x and writes dx (+ 8 bytes of statistics per row).  Each call works on fresh > L2 operands.
+bwd reads dy and x and writes dx (+ 8 bytes of statistics per row); dwconv fwd reads x / writes y, bwd reads x, dy / writes dx.  Each call works on fresh > L2 operands.
 """
 import json
 import os
@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import torch  # noqa: E402
 
+from nnuzoo_b200.dwconv import dwconv3x3_silu  # noqa: E402
 from nnuzoo_b200.norm import LayerNormFn  # noqa: E402
 from nnuzoo_b200.proj import proj_wgrad  # noqa: E402
 
@@ -24,8 +25,13 @@ def peak():
         return 6650.0
 
 
+ONCE = bool(os.environ.get("NZ_PROF_ONCE"))   # one launch per kernel and shape: for `ncu --set full`
+
+
 def timed(fn, n=10):
-    for _ in range(3):
+    if ONCE:
+        n = 1
+    for _ in range(0 if ONCE else 3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -70,6 +76,20 @@ def main():
         bb = rows * (C * (2 * si + so) + 8)
         print(f"layernorm C={C:4d} rows={rows:8d} {str(din)[6:]:>8s}->{str(dout)[6:]:<8s}: fwd {ms_f:6.3f} ms {bf / ms_f / 1e6:6.0f} GB/s "
               f"({100 * bf / ms_f / 1e6 / pk:4.1f} %)  bwd {ms_fb:6.3f} ms {bb / ms_fb / 1e6:6.0f} GB/s ({100 * bb / ms_fb / 1e6 / pk:4.1f} %)")
+        del x, gy, y
+    for D, res in [(32, 512), (64, 256), (128, 128), (256, 64)]:
+        x = torch.randn(B, D, res, res, device="cuda").bfloat16().requires_grad_(True)
+        w = torch.randn(D, 1, 3, 3, device="cuda", requires_grad=True)
+        b = torch.zeros(D, device="cuda", requires_grad=True)
+        gy = torch.randn_like(x)
+        with torch.no_grad():
+            ms_f = timed(lambda: dwconv3x3_silu(x, w, b))
+        y = dwconv3x3_silu(x, w, b)
+        ms_b = timed(lambda: torch.autograd.grad(y, (x, w, b), gy, retain_graph=True))
+        n = x.numel() * 2
+        print(f"dwconv3x3+silu D={D:3d} {res}x{res} bf16: fwd {ms_f:6.3f} ms {2 * n / ms_f / 1e6:6.0f} GB/s "
+              f"({100 * 2 * n / ms_f / 1e6 / pk:4.1f} %)  bwd {ms_b:6.3f} ms {3 * n / ms_b / 1e6:6.0f} GB/s "
+              f"({100 * 3 * n / ms_b / 1e6 / pk:4.1f} %)")
         del x, gy, y
 
 
