@@ -63,7 +63,8 @@ typedef struct NzScanDesc {
   int32_t dtype;          /* NZ_F32 / NZ_BF16 / NZ_F16                             */
   int32_t delta_softplus; /* 0 / 1                                                 */
   int32_t force_generic;  /* 1: never use the TMA path (testing)                   */
-  int32_t reserved0;
+  int32_t out_f32;        /* 1 with a 16-bit dtype: `out` is fp32 (16-bit operands in, fp32 result out -- SS2D under
+                             autocast keeps an fp32 out_y, m2net.py:185-200); ignored for NZ_F32 and by nz_scan_bwd */
 
   /* ---- forward inputs (selective_scan_cuda.fwd arguments) ---- */
   const void* u;            /* (batch, dim, L)                 */

@@ -30,7 +30,7 @@ class NzScanDesc(ctypes.Structure):
     _fields_ = [
         ("batch", _i32), ("dim", _i32), ("dstate", _i32), ("ngroups", _i32),
         ("seqlen", _i64),
-        ("dtype", _i32), ("delta_softplus", _i32), ("force_generic", _i32), ("reserved0", _i32),
+        ("dtype", _i32), ("delta_softplus", _i32), ("force_generic", _i32), ("out_f32", _i32),
         ("u", _vp), ("delta", _vp), ("A", _vp), ("B", _vp), ("C", _vp), ("D", _vp), ("z", _vp),
         ("delta_bias", _vp),
         ("u_stride", _i64 * 2), ("delta_stride", _i64 * 2), ("z_stride", _i64 * 2),

@@ -170,7 +170,9 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   a.carry = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d->workspace) + kWsHeader);
   a.softplus = d->delta_softplus;
   const size_t es = esize(d->dtype);
-  a.vec_out = d->out && aligned16(d->out) && (d->out_stride[0] * es) % 16 == 0 && (d->out_stride[1] * es) % 16 == 0;
+  a.out_f32 = (d->out_f32 && d->dtype != NZ_F32) ? 1 : 0;
+  const size_t eo = a.out_f32 ? 4 : es;
+  a.vec_out = d->out && aligned16(d->out) && (d->out_stride[0] * eo) % 16 == 0 && (d->out_stride[1] * eo) % 16 == 0;
   a.vec_grad = (d->seqlen * es) % 16 == 0 && (d->seqlen % 4 == 0) && (!d->du || aligned16(d->du)) &&
                (!d->ddelta || aligned16(d->ddelta)) && (!d->dz || aligned16(d->dz)) && (!d->dB || aligned16(d->dB)) &&
                (!d->dC || aligned16(d->dC));

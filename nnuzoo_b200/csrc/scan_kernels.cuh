@@ -93,6 +93,7 @@ struct alignas(64) ScanKArgs {
                    // (priority inversion: the whole chain stalls until that CTA comes round)
   int skew;      // states the later chunk's tile must be ahead before a dependent tile starts polling
   int vec_out;   // out rows 16-byte aligned -> vector stores
+  int out_f32;   // 16-bit instantiations only: `out` is fp32 (NzScanDesc::out_f32)
   int vec_grad;  // du/ddelta/dz and dB/dC rows 16-byte aligned
 };
 
@@ -629,7 +630,13 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
 #pragma unroll
       for (int i = 0; i < M; ++i) y[i] *= zz[i] * sigmoid_f(zz[i]);
     }
-    if (row_ok) stg_items<T, M>(outrow, y, t0, a.L, a.vec_out != 0);
+    if (row_ok) {
+      if (sizeof(T) == 2 && a.out_f32)
+        stg_items<float, M>(reinterpret_cast<float*>(a.out) + (long)q.b * a.o_bs + (long)d * a.o_ds, y, t0, a.L,
+                            a.vec_out != 0);
+      else
+        stg_items<T, M>(outrow, y, t0, a.L, a.vec_out != 0);
+    }
     if (a.trace && tid == 0) {
       unsigned long long* tr = a.trace + (long)t * 8;
       tr[6] = tr_recv0;

@@ -86,8 +86,11 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
-                return_last_state=False):
+                return_last_state=False, out_dtype=None):
         _check_inputs(u, delta, A, B, C, D, z, delta_bias)
+        out_f32 = out_dtype == torch.float32 and u.dtype != torch.float32
+        if out_dtype is not None and out_dtype != u.dtype and not out_f32:
+            raise TypeError("out_dtype must be u's dtype or torch.float32")
         ctx.in_dtypes = tuple(None if t is None else t.dtype for t in (delta, A, B, C, D, z, delta_bias))
         # :19-30 -- only the innermost stride has to be 1; outer strides are passed to the kernel
         if u.stride(-1) != 1:
@@ -124,10 +127,11 @@ class SelectiveScanFn(torch.autograd.Function):
         lib = _native.lib()
         _native.bind_device(u.device.index)
         nchunks = (L + _native.NZ_CHUNK - 1) // _native.NZ_CHUNK
-        out = torch.empty((batch, dim, L), dtype=u.dtype, device=u.device)
+        out = torch.empty((batch, dim, L), dtype=torch.float32 if out_f32 else u.dtype, device=u.device)
         x = torch.empty((batch, dim, nchunks, N), dtype=torch.float32, device=u.device)
         desc = NzScanDesc()
         ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC)
+        desc.out_f32 = int(out_f32)
         desc.out = _ptr(out)
         desc.out_stride[0], desc.out_stride[1] = out.stride(0), out.stride(1)
         desc.x = _ptr(x)
@@ -184,11 +188,17 @@ class SelectiveScanFn(torch.autograd.Function):
         t_delta, t_A, t_B, t_C, t_D, t_z, t_bias = ctx.in_dtypes
         cast = lambda g, t: g if g is None or g.dtype == t else g.to(t)  # noqa: E731
         return (du, cast(ddelta, t_delta), cast(dA, t_A), cast(dB, t_B), cast(dC, t_C), cast(dD, t_D),
-                cast(dz, t_z), cast(dbias, t_bias), None, None)  # order of :69-74
+                cast(dz, t_z), cast(dbias, t_bias), None, None, None)  # order of :69-74
 
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
-                      return_last_state=False):
+                      return_last_state=False, *, out_dtype=None):
     """if return_last_state is True, returns (out, last_state); last_state has shape
-    (batch, dim, dstate) and carries no gradient (selective_scan_interface.py:77-83)."""
-    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
+    (batch, dim, dstate) and carries no gradient (selective_scan_interface.py:77-83).
+
+    Extension (keyword-only, not in the reference signature): ``out_dtype=torch.float32`` with 16-bit operands
+    returns the fp32 result without the operands ever being widened in HBM -- what SS2D under autocast needs, where
+    the reference first copies xs / dts / Bs / Cs to fp32 (m2net.py:185-188) to get an fp32 out_y (:200).  The
+    arithmetic is the same fp32 arithmetic on the same operand values; the backward reads ``dout`` in the operand
+    dtype."""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state, out_dtype)

@@ -122,9 +122,18 @@ class _CrossScanSSM(nn.Module):
         x_dbl = grouped_proj(xs, self.x_proj_weight)            # einsum "b k d l, k c d -> b k c l", m2net.py:179
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                                  # :181
         dts = grouped_proj(dts, self.dt_projs_weight)           # einsum "b k r l, k d r -> b k d l", :182
+        As = -torch.exp(self.A_logs.float()).view(-1, N)                                    # :190
+        if self.selective_scan is selective_scan_fn and xs.dtype != torch.float32 and dts.dtype == xs.dtype:
+            # autocast: 16-bit operands go to the kernel as they are, the result comes back in fp32 -- the same
+            # numbers as the reference's "widen everything, then scan" (:185-191) without the four fp32 copies
+            out_y = selective_scan_fn(
+                xs.view(bsz, -1, L), dts.contiguous().view(bsz, -1, L), As, Bs, Cs, self.Ds.float().view(-1), z=None,
+                delta_bias=self.dt_projs_bias.float().view(-1), delta_softplus=True, return_last_state=False,
+                out_dtype=torch.float32).view(bsz, K, -1, L)
+            return cross_merge(out_y, spatial, merge_mode)
         out_y = self.selective_scan(
             xs.float().view(bsz, -1, L), dts.contiguous().float().view(bsz, -1, L),        # :185-186
-            -torch.exp(self.A_logs.float()).view(-1, N),                                    # :190
+            As,
             Bs.float(), Cs.float(),                                                         # :187-188 (views)
             self.Ds.float().view(-1), z=None,
             delta_bias=self.dt_projs_bias.float().view(-1),

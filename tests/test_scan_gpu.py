@@ -283,3 +283,36 @@ def test_host_entry_point_matches_device_path():
              "dC": grads["dC"], "dA": grads["dA"], "dD": grads["dD"], "db": grads["ddelta_bias"]}
     for k, ref in pairs.items():
         assert rel_err(res[k], ref.detach().float().cpu().numpy()) < 1e-5, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_16bit_operands_fp32_result_equals_widened_fp32_scan(dtype):
+    """out_dtype=float32 extension (SS2D under autocast): 16-bit operands in, fp32 out.  Same operand values, same
+    fp32 arithmetic as the reference's widen-then-scan (m2net.py:185-200): outputs agree to fp32 rounding; gradients
+    to the 16-bit tolerance (dout is read, du / ddelta are written in the operand dtype)."""
+    from nnuzoo_b200 import selective_scan_fn
+    torch.manual_seed(5)
+    Bn, K, D, N, L = 2, 4, 32, 16, 1536
+    mk = lambda *s: torch.randn(*s, device="cuda")  # noqa: E731
+    u16 = mk(Bn, K * D, L).to(dtype)
+    dl16 = (0.5 * mk(Bn, K * D, L)).to(dtype)
+    xdbl = mk(Bn, K, 2 + 2 * N, L).to(dtype)
+    B16, C16 = xdbl[:, :, 2:2 + N], xdbl[:, :, 2 + N:]          # strided split views, as SS2D hands them over
+    A = -torch.exp(torch.log(torch.arange(1, N + 1, device="cuda").float()).repeat(K * D, 1) + 0.1 * mk(K * D, N))
+    Dp, bias = 1 + 0.1 * mk(K * D), -2 + 0.3 * mk(K * D)
+    gout = mk(Bn, K * D, L)
+
+    def run(u, dl, Bm, Cm, **kw):
+        leaves = [t.detach().clone().requires_grad_(True) for t in (u, dl, Bm, Cm)]
+        p = [t.detach().clone().requires_grad_(True) for t in (A, Dp, bias)]
+        out = selective_scan_fn(leaves[0], leaves[1], p[0], leaves[2], leaves[3], p[1], None, p[2], True, **kw)
+        out.backward(gout.to(out.dtype))
+        return out.detach(), [t.grad for t in leaves + p]
+
+    o_mix, g_mix = run(u16, dl16, B16, C16, out_dtype=torch.float32)
+    o_ref, g_ref = run(u16.float(), dl16.float(), B16.float(), C16.float())
+    assert o_mix.dtype == torch.float32
+    assert rel_err(o_mix.cpu().numpy(), o_ref.cpu().numpy()) < 1e-5
+    for a, b in zip(g_mix, g_ref):
+        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < 2e-2
