@@ -50,7 +50,9 @@ extern "C" {
 
 /* The forward saves the state h every NZ_CHUNK steps ("x" of the reference ABI); the backward
  * recomputes inside a chunk from it. */
+#ifndef NZ_CHUNK
 #define NZ_CHUNK 128
+#endif
 #define NZ_MAX_DSTATE 16
 
 typedef struct NzScanDesc {

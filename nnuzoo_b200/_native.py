@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NNUZOO_B200_LIB") or os.path.join(_HERE, "lib", "libnnuzoo_b200.so")
 
 NZ_F32, NZ_BF16, NZ_F16 = 0, 1, 2
-NZ_CHUNK = 128
+NZ_CHUNK = int(os.environ.get("NNUZOO_B200_CHUNK", "128"))   # tuning builds may use another interval
 NZ_MAX_DSTATE = 16
 ABI_VERSION = 2
 WS_HEADER = 256

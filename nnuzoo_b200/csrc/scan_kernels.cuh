@@ -34,6 +34,7 @@
 //     (one shuffle per value) and then across the warps of the CTA in shared memory.
 #pragma once
 
+#include "../../include/nnuzoo_b200.h"  // NZ_CHUNK
 #include "nz_common.cuh"
 
 #ifndef NZ_FWD_UNROLL
@@ -65,7 +66,7 @@
 
 namespace nz {
 
-constexpr int kCkpt = 128;  // == NZ_CHUNK of the C ABI: steps between two checkpoints of h
+constexpr int kCkpt = NZ_CHUNK;  // the C ABI's checkpoint interval: steps between two saved states h
 
 struct alignas(64) ScanKArgs {
   CUtensorMap tm_u, tm_delta, tm_z, tm_dout, tm_B, tm_C;
@@ -679,8 +680,11 @@ __device__ __forceinline__ void red_add_v4(float* dst, float4 v) {
                : "memory");
 }
 
+#ifndef NZ_BWD_MINB
+#define NZ_BWD_MINB 2  // resident CTAs per SM the backward is compiled for
+#endif
 template <typename T, int M, int LPR, int WARPS, bool kTMA, bool kHasZ>
-__global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : 2)
+__global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4) ? 1 : NZ_BWD_MINB)
     scan_bwd_kernel(const __grid_constant__ ScanKArgs a) {
   using Cfg = ScanCfg<T, M, LPR, WARPS, kHasZ, true>;
   constexpr int R = Cfg::R, TL = Cfg::TL, ROWB = Cfg::ROWB, SEGB = Cfg::SEGB, RPW = Cfg::RPW;
