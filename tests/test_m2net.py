@@ -43,7 +43,32 @@ def _run(net, rec, device):
     return x, outs
 
 
+def _dice_per_label(seg_pred, seg_ref, labels):
+    """Dice = 2 TP / (2 TP + FP + FN) per foreground label (evaluation/evaluate_predictions.py:190-197)."""
+    out = []
+    for r in labels:
+        mp, mr = seg_pred == r, seg_ref == r
+        tp, fp, fn = int((mp & mr).sum()), int((mp & ~mr).sum()), int((~mp & mr).sum())
+        out.append(float("nan") if tp + fp + fn == 0 else 2 * tp / (2 * tp + fp + fn))
+    return np.array(out)
+
+
+def _check_dice(outs, rec):
+    """north_star's end-to-end criterion: Dice within 0.005 of the reference on identical synthetic volumes.  The
+    segmentation is argmax of the full-resolution logits d0; "ground truth" is a seeded label map that agrees with the
+    reference's own segmentation on ~70 % of the pixels, so the Dice values are neither 0 nor 1."""
+    ref_seg = rec["d0"].argmax(1)
+    our_seg = outs[0].detach().float().cpu().numpy().argmax(1)
+    rng = np.random.RandomState(3)
+    gt = np.where(rng.rand(*ref_seg.shape) < 0.7, ref_seg, rng.randint(0, 4, ref_seg.shape))
+    d_ref, d_our = _dice_per_label(ref_seg, gt, (1, 2, 3)), _dice_per_label(our_seg, gt, (1, 2, 3))
+    assert np.all(np.isfinite(d_ref)) and d_ref.min() > 0.05 and d_ref.max() < 0.95
+    assert np.abs(d_ref - d_our).max() <= 0.005, (d_ref, d_our)
+    assert _dice_per_label(our_seg, ref_seg, (1, 2, 3)).min() >= 0.995
+
+
 def _check(net, x, outs, rec, tol, gtol=2e-2):
+    _check_dice(outs, rec)
     for i, o in enumerate(outs):
         assert tuple(o.shape) == rec[f"d{i}"].shape
         assert rel_err(o.detach().cpu().numpy(), rec[f"d{i}"]) < tol, f"d{i}"

@@ -10,7 +10,8 @@ CSRC = os.path.join(ROOT, "nnuzoo_b200", "csrc")
 OUT = os.path.join(ROOT, "tune_variants")
 BASE = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
         "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-I", os.path.join(ROOT, "include")]
-SRCS = ["capi.cu", "cross_kernels.cu", "conv1d_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", "scan_inst_f16.cu"]
+sys.path.insert(0, ROOT)
+from nnuzoo_b200.build import SOURCES as SRCS  # noqa: E402  (every translation unit of the library)
 
 
 def build(spec):
