@@ -215,6 +215,25 @@ int nz_dwconv3x3_bwd(const void* x, const void* dy, const float* weight, const f
                      void* stream);
 
 /*
+ * SS2D's post-scan chain fused (2-D, 4 directions): CrossMerge -> (B, L, D) -> LayerNorm over D -> * SiLU(z)
+ * (m2net.py:202-206, :218-221).  out_y (batch, 4, D, L) fp32 as nz_scan_fwd writes it; z rows of D contiguous elements
+ * (z_stride = {batch, position} element strides: the chunk view of in_proj's output goes in as it is); gamma / beta fp32
+ * (may be NULL); out (batch, L, D) contiguous of out_dtype.  The forward also writes what the backward needs: the merged
+ * y (batch, L, D) fp32 -- bit-identical to nz_cross_merge -- and the row statistics mean / rstd (batch * L).
+ * Backward: dout (batch, L, D) of out_dtype -> d_out_y (batch, 4, D, L) of grad_dtype (fp32, or the scan's 16-bit operand
+ * dtype so that nz_scan_bwd reads it directly), dz (batch, L, D) contiguous of z_dtype, dgamma / dbeta ACCUMULATED INTO.
+ * D: multiple of 32, 32..256 (nz_ss2d_epilogue_supported).
+ */
+int nz_ss2d_epilogue_supported(int32_t D);
+int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma, const float* beta,
+                         void* out, float* y_merged, float* mean, float* rstd, int32_t z_dtype, int32_t out_dtype,
+                         int32_t batch, int32_t D, int32_t H, int32_t W, float eps, void* stream);
+int nz_ss2d_epilogue_bwd(const void* dout, const float* y_merged, const float* mean, const float* rstd, const void* z,
+                         const int64_t* z_stride, const float* gamma, const float* beta, void* d_out_y, void* dz,
+                         float* dgamma, float* dbeta, int32_t z_dtype, int32_t out_dtype, int32_t grad_dtype,
+                         int32_t batch, int32_t D, int32_t H, int32_t W, void* stream);
+
+/*
  * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):
  * every pointer in `desc` is a HOST pointer, strides as above; the call stages host -> device,
  * runs nz_scan_fwd (and nz_scan_bwd when desc->dout != NULL) and copies the results back,

@@ -107,6 +107,14 @@ def lib():
                 L.nz_dwconv3x3_fwd.restype = ctypes.c_int
                 L.nz_dwconv3x3_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
                 L.nz_dwconv3x3_bwd.restype = ctypes.c_int
+                L.nz_ss2d_epilogue_supported.argtypes = [_i32]
+                L.nz_ss2d_epilogue_supported.restype = ctypes.c_int
+                L.nz_ss2d_epilogue_fwd.argtypes = [_vp, _vp, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32,
+                                                   _i32, _i32, _i32, _i32, ctypes.c_float, _vp]
+                L.nz_ss2d_epilogue_fwd.restype = ctypes.c_int
+                L.nz_ss2d_epilogue_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _vp,
+                                                   _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
+                L.nz_ss2d_epilogue_bwd.restype = ctypes.c_int
                 L.nz_sizeof_conv1d_desc.restype = _i64
                 if L.nz_sizeof_conv1d_desc() != ctypes.sizeof(NzConv1dDesc):
                     raise NativeLibraryError("NzConv1dDesc layout differs between _native.py and the .so")

@@ -18,7 +18,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libnnuzoo_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["capi.cu", "cross_kernels.cu", "conv1d_kernels.cu", "proj_kernels.cu", "norm_kernels.cu", "dwconv_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", "scan_inst_f16.cu"]
+SOURCES = ["capi.cu", "cross_kernels.cu", "conv1d_kernels.cu", "proj_kernels.cu", "norm_kernels.cu", "dwconv_kernels.cu", "epilogue_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", "scan_inst_f16.cu"]
 HEADERS = ["nz_common.cuh", "scan_kernels.cuh", "scan_inst.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-warn-spills"]

@@ -1,0 +1,102 @@
+"""SS2D core as ONE autograd node: selective scan -> CrossMerge -> LayerNorm -> * SiLU(z)   (2-D, 4 directions).
+
+Reference statements: nnunetv2/nets/m2net.py:193-206 (scan + merge), :218-221 (sum, transpose, out_norm, gate).
+The node calls ``nz_scan_fwd`` and then ``nz_ss2d_epilogue_fwd`` (csrc/epilogue_kernels.cu); its backward calls
+``nz_ss2d_epilogue_bwd`` -- which hands the four permuted copies of dy to the scan in the scan's own operand dtype -- and
+then ``nz_scan_bwd``.  Being one node is what allows that hand-over: between separate autograd nodes the engine would cast
+the 16-bit gradient back to out_y's fp32.  CUDA only, no fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _native
+from .selective_scan_interface import SelectiveScanFn
+
+_DT = {torch.float32: _native.NZ_F32, torch.bfloat16: _native.NZ_BF16, torch.float16: _native.NZ_F16}
+
+
+def _vp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+class _InnerCtx:
+    """Stands in for the autograd ctx of SelectiveScanFn, whose forward / backward bodies are reused as they are."""
+
+    saved_tensors = ()
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+    def mark_non_differentiable(self, *tensors):
+        pass
+
+
+def supported(d_inner: int) -> bool:
+    return bool(_native.lib().nz_ss2d_epilogue_supported(int(d_inner)))
+
+
+class SS2DCoreFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xs, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype):
+        bsz, K, D, L = xs.shape
+        if K != 4 or H * W != L:
+            raise ValueError("ss2d_core: xs must be (B, 4, D, H*W)")
+        if z.shape != (bsz, H, W, D) or z.stride(3) != 1 or z.stride(1) != W * z.stride(2) or z.dtype not in _DT:
+            raise ValueError("ss2d_core: z must be a (B, H, W, D) tensor with unit channel stride and collapsible H, W")
+        inner = _InnerCtx()
+        scan_out = torch.float32 if xs.dtype != torch.float32 else None
+        out_y = SelectiveScanFn.forward(inner, xs.view(bsz, K * D, L), dts.view(bsz, K * D, L), As, Bs, Cs, Ds, None,
+                                        dt_bias, True, False, scan_out)
+        dev = xs.device
+        out = torch.empty((bsz, H, W, D), dtype=out_dtype, device=dev)
+        ym = torch.empty((bsz, L, D), dtype=torch.float32, device=dev)
+        mean = torch.empty(bsz * L, dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        g32 = gamma.float().contiguous() if gamma is not None else None
+        b32 = beta.float().contiguous() if beta is not None else None
+        zs = (ctypes.c_int64 * 2)(z.stride(0), z.stride(2))
+        _native.bind_device(dev.index)
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(_native.lib().nz_ss2d_epilogue_fwd(_vp(out_y), _vp(z), zs, _vp(g32), _vp(b32), _vp(out), _vp(ym),
+                                                         _vp(mean), _vp(rstd), _DT[z.dtype], _DT[out_dtype], bsz, D, H, W,
+                                                         float(eps), st), "nz_ss2d_epilogue_fwd")
+        ctx.inner = inner
+        ctx.save_for_backward(ym, mean, rstd, z, g32, b32)
+        ctx.dims = (bsz, K, D, H, W)
+        ctx.dtypes = (xs.dtype, out_dtype, gamma.dtype if gamma is not None else None,
+                      beta.dtype if beta is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ym, mean, rstd, z, g32, b32 = ctx.saved_tensors
+        bsz, K, D, H, W = ctx.dims
+        op_dtype, out_dtype, gdt, bdt = ctx.dtypes
+        L = H * W
+        dev = ym.device
+        dout = dout.contiguous()
+        if dout.dtype != out_dtype:
+            dout = dout.to(out_dtype)
+        d_out_y = torch.empty((bsz, K * D, L), dtype=op_dtype, device=dev)   # the scan's operand dtype
+        dz = torch.empty((bsz, H, W, D), dtype=z.dtype, device=dev)
+        dg = torch.zeros(D, dtype=torch.float32, device=dev) if g32 is not None else None
+        db = torch.zeros(D, dtype=torch.float32, device=dev) if b32 is not None else None
+        zs = (ctypes.c_int64 * 2)(z.stride(0), z.stride(2))
+        _native.bind_device(dev.index)
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(_native.lib().nz_ss2d_epilogue_bwd(_vp(dout), _vp(ym), _vp(mean), _vp(rstd), _vp(z), zs, _vp(g32),
+                                                         _vp(b32), _vp(d_out_y), _vp(dz), _vp(dg), _vp(db), _DT[z.dtype],
+                                                         _DT[out_dtype], _DT[op_dtype], bsz, D, H, W, st),
+                      "nz_ss2d_epilogue_bwd")
+        du, ddelta, dA, dB, dC, dD, _dz, dbias, *_ = SelectiveScanFn.backward(ctx.inner, d_out_y)
+        ctx.inner = None
+        return (du.view(bsz, K, D, L), ddelta.view(bsz, K, D, L), dA, dB, dC, dD, dbias, dz,
+                dg.to(gdt) if dg is not None else None, db.to(bdt) if db is not None else None, None, None, None, None)
+
+
+def ss2d_core(xs, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype):
+    """xs, dts (B, 4, D, L) contiguous; Bs, Cs (B, 4, N, L) (strided views fine); z (B, H, W, D) -> (B, H, W, D)."""
+    return SS2DCoreFn.apply(xs, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, int(H), int(W), float(eps), out_dtype)

@@ -11,6 +11,8 @@ Differences are confined to *how* forward_core executes:
   * the scan is nnuzoo_b200.selective_scan_fn (no mamba_ssm dependency);
   * B/C are handed to the scan as the strided split views they are (no .contiguous());
   * SS2D's depthwise 3x3 conv + SiLU is one kernel each way (nnuzoo_b200.dwconv);
+  * SS2D (2-D) runs scan -> CrossMerge -> out_norm -> SiLU(z) gate as one autograd node with a fused epilogue kernel
+    (nnuzoo_b200.fused; ``fuse_epilogue = False`` restores the op-by-op path);
   * the two projection einsums run as batched GEMMs whose weight gradient is our own reduction kernel
     (nnuzoo_b200.proj).
 """
@@ -22,6 +24,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused
 from .cross_scan import cross_merge, cross_scan
 from .dwconv import dwconv3x3_silu
 from .norm import LayerNorm
@@ -42,6 +45,8 @@ class _ConvOnly(nn.Sequential):
 
 class _CrossScanSSM(nn.Module):
     """Parameters and forward_core shared by SS2D (K = 4) and SSND (K = 4 or 6)."""
+
+    fuse_epilogue = True   # SS2D: run scan -> merge -> out_norm -> gate as one autograd node (nnuzoo_b200.fused)
 
     def _init_ssm(self, d_model, d_state, expand, dt_rank, dt_min, dt_max, dt_init, dt_scale, dt_init_floor,
                   bias, dropout, k, factory_kwargs):
@@ -112,17 +117,23 @@ class _CrossScanSSM(nn.Module):
         p._no_weight_decay = True
         return p
 
-    def forward_core(self, x: torch.Tensor, merge_mode: str = "reference") -> torch.Tensor:
-        """x (B, D, *spatial) -> merged y (B, D, L) fp32 (m2net.py:170-206 + :218; ssnd2net.py:239-298)."""
-        bsz = x.shape[0]
-        spatial = tuple(x.shape[2:])
-        K, N, R = self.k, self.d_state, self.dt_rank
+    def _scan_operands(self, x: torch.Tensor):
+        """x (B, D, *spatial) -> xs, dts (B, K, D, L), As (K*D, N), Bs, Cs (B, K, N, L) views  (m2net.py:172-190)."""
+        N, R = self.d_state, self.dt_rank
         xs = cross_scan(x)                                                    # (B, K, D, L)
-        L = xs.shape[-1]
         x_dbl = grouped_proj(xs, self.x_proj_weight)            # einsum "b k d l, k c d -> b k c l", m2net.py:179
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                                  # :181
         dts = grouped_proj(dts, self.dt_projs_weight)           # einsum "b k r l, k d r -> b k d l", :182
         As = -torch.exp(self.A_logs.float()).view(-1, N)                                    # :190
+        return xs, dts, As, Bs, Cs
+
+    def forward_core(self, x: torch.Tensor, merge_mode: str = "reference") -> torch.Tensor:
+        """x (B, D, *spatial) -> merged y (B, D, L) fp32 (m2net.py:170-206 + :218; ssnd2net.py:239-298)."""
+        bsz = x.shape[0]
+        spatial = tuple(x.shape[2:])
+        K, N = self.k, self.d_state
+        xs, dts, As, Bs, Cs = self._scan_operands(x)
+        L = xs.shape[-1]
         if self.selective_scan is selective_scan_fn and xs.dtype != torch.float32 and dts.dtype == xs.dtype:
             # autocast: 16-bit operands go to the kernel as they are, the result comes back in fp32 -- the same
             # numbers as the reference's "widen everything, then scan" (:185-191) without the four fp32 copies
@@ -140,6 +151,20 @@ class _CrossScanSSM(nn.Module):
             delta_softplus=True, return_last_state=False,
         ).view(bsz, K, -1, L)
         return cross_merge(out_y, spatial, merge_mode)
+
+    def _fused_core(self, x: torch.Tensor, z: torch.Tensor):
+        """Scan + merge + out_norm + gate as one node (nnuzoo_b200.fused); None when the shape is outside its cover."""
+        if (not self.fuse_epilogue or self.k != 4 or x.dim() != 4 or not x.is_cuda
+                or self.selective_scan is not selective_scan_fn or not fused.supported(self.d_inner)):
+            return None
+        xs, dts, As, Bs, Cs = self._scan_operands(x)
+        if dts.dtype != xs.dtype or z.stride(-1) != 1 or z.stride(1) != z.shape[2] * z.stride(2):
+            return None
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else xs.dtype
+        H, W = x.shape[2:]
+        return fused.ss2d_core(xs, dts.contiguous(), As, Bs, Cs, self.Ds.float().view(-1),
+                               self.dt_projs_bias.float().view(-1), z, self.out_norm.weight, self.out_norm.bias, H, W,
+                               self.out_norm.eps, out_dtype)
 
     def _finish(self, y, z, bsz, spatial):
         y = y.transpose(1, 2).contiguous().view(bsz, *spatial, -1)     # m2net.py:219
@@ -174,6 +199,10 @@ class SS2D(_CrossScanSSM):
             x = dwconv3x3_silu(x, c.weight, c.bias)                      # :214-215 as one kernel
         else:
             x = self.act(c(x))
+        g = self._fused_core(x, z)
+        if g is not None:                                                # :193-206, :218-221 as one node
+            out = self.out_proj(g)                                       # :222
+            return out if self.dropout is None else self.dropout(out)
         y = self.forward_core(x)
         return self._finish(y, z, bsz, (H, W))
 
