@@ -222,7 +222,7 @@ int nz_dwconv3x3_bwd(const void* x, const void* dy, const float* weight, const f
  * y (batch, L, D) fp32 -- bit-identical to nz_cross_merge -- and the row statistics mean / rstd (batch * L).
  * Backward: dout (batch, L, D) of out_dtype -> d_out_y (batch, 4, D, L) of grad_dtype (fp32, or the scan's 16-bit operand
  * dtype so that nz_scan_bwd reads it directly), dz (batch, L, D) contiguous of z_dtype, dgamma / dbeta ACCUMULATED INTO.
- * D: multiple of 32, 32..256 (nz_ss2d_epilogue_supported).
+ * D: 32, 64, 128 or 256 (nz_ss2d_epilogue_supported) -- d_model 16 .. 128, every SS2D of M2Net.
  */
 int nz_ss2d_epilogue_supported(int32_t D);
 int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma, const float* beta,

@@ -8,15 +8,20 @@
 // and z once, write the gated result once (+ the merged y in channels-last order and the row statistics the backward
 // needs); backward: read dout, y, z once, write dz and the four permuted copies of dy once.
 //
-// A CTA owns a TH x TW tile of spatial positions and all D channels of it in shared memory ([position][D + 1] fp32, the
-// odd pitch makes both access patterns conflict-free).  The row-major directions (k0, k2) are read / written in runs
+// A CTA owns a TH x TW tile of spatial positions and all D channels of it in shared memory ([channel][TH x (TW + 1)]
+// fp32 with an odd plane pitch: walking w, walking h and walking channels are all (nearly) conflict-free).
+// The row-major directions (k0, k2) are read / written in runs
 // of TW elements, the column-major ones (k1, k3) in runs of TH, so every direction moves whole sectors; the four values
 // are added in the reference's order ((y0 + flip y2) + T y1) + T flip y3, fp32, so the merged y is bit-identical to
-// nz_cross_merge.  LayerNorm: one warp per position, lanes strided over channels, fp32 two-pass statistics.
+// nz_cross_merge.  LayerNorm / gate: D / 8 adjacent lanes per position, 8 channels (one 16-byte vector) per lane, so a
+// warp works on 32 / (D / 8) positions at once and every warp makes exactly four passes per tile (TH * TW * D = 8192);
+// fp32 two-pass statistics.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "../../include/nnuzoo_b200.h"
 
@@ -41,14 +46,55 @@ __device__ __forceinline__ void e_st<__nv_bfloat16>(__nv_bfloat16* p, float v) {
 template <>
 __device__ __forceinline__ void e_st<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// 8 consecutive elements <-> 8 floats (16 bytes of a 16-bit type, 32 bytes of fp32)
+template <typename T>
+__device__ __forceinline__ void ld8(const T* __restrict__ p, float (&f)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+  } else {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value) {
+        f[2 * i] = __uint_as_float(w[i] << 16), f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      } else {
+        const float2 q = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        f[2 * i] = q.x, f[2 * i + 1] = q.y;
+      }
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st8(T* __restrict__ p, const float (&f)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        const __nv_bfloat162 q = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&q);
+      } else {
+        const __half2 q = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&q);
+      }
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__device__ __forceinline__ float group_sum(float v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
 constexpr int kEpThreads = 256;
-constexpr int kEpMaxDPL = 8;  // channels per lane: D <= 256
+constexpr int kEpCPL = 8;     // channels per lane in the per-position phase (one 16-byte vector of a 16-bit type)
+constexpr int kEpPasses = 4;  // P * D = 8192: every warp makes 4 passes over (32 / G) positions, G = D / 8 lanes each
 
 struct EpArgs {
   // forward
@@ -64,7 +110,8 @@ struct EpArgs {
   void* d_out_y;     // (B, 4, D, L), TG
   void* dz;          // (B, L, D) contiguous, TZ
   float *dgamma, *dbeta;
-  int B, D, H, W, TH, TW;
+  int B, D, H, W, TH, TW;  // TH, TW powers of two, TH * TW * D = 8192
+  int lTH, lTW;            // their log2
   float eps;
 };
 
@@ -86,75 +133,89 @@ __device__ __forceinline__ bool ep_tile(const EpArgs& a, long tile, EpTile* t) {
 
 template <typename TZ, typename TO>
 __global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_fwd_kernel(EpArgs a) {
-  extern __shared__ float sm[];  // [P][D + 1]
-  const int D = a.D, P = a.TH * a.TW, pitch = D + 1;
+  extern __shared__ float sm[];  // [D][S], S = TH * (TW + 1) made odd: position (ph, pw) sits at ph * (TW + 1) + pw
+  const int D = a.D, P = a.TH * a.TW, lP = a.lTH + a.lTW, S = (a.TH * (a.TW + 1)) | 1, TW1 = a.TW + 1;
   const long L = (long)a.H * a.W;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int dpl = D / 32;
-  float gm[kEpMaxDPL], bt[kEpMaxDPL];
+  const int G = D / kEpCPL;           // lanes per position (4 .. 32)
+  const int ppw = 32 / G;             // positions a warp handles per pass
+  const int lg = lane % G, lp = lane / G;
+  const int c0 = lg * kEpCPL;
+  float gm[kEpCPL], bt[kEpCPL];
 #pragma unroll
-  for (int i = 0; i < kEpMaxDPL; ++i)
-    if (i < dpl) gm[i] = a.gamma ? a.gamma[lane + 32 * i] : 1.f, bt[i] = a.beta ? a.beta[lane + 32 * i] : 0.f;
+  for (int i = 0; i < kEpCPL; ++i) gm[i] = a.gamma ? a.gamma[c0 + i] : 1.f, bt[i] = a.beta ? a.beta[c0 + i] : 0.f;
+  const TZ* __restrict__ zp = static_cast<const TZ*>(a.z);
+  TO* __restrict__ outp = static_cast<TO*>(a.out);
+  float* __restrict__ ymp = a.ym;
+  const float invD = 1.f / (float)D;
   EpTile tl;
   for (long tile = blockIdx.x; ep_tile(a, tile, &tl); tile += gridDim.x) {
-    const float* oy = a.out_y + tl.b * 4 * D * L;
+    const float* __restrict__ oy = a.out_y + tl.b * 4 * D * L;
     const long ks = (long)D * L;
-    // row-major directions: y0[p] + y2[L-1-p]
+    // row-major directions: y0[p] + y2[L-1-p]      (P * D / 256 = 32 trips)
+#pragma unroll 8
     for (int i = t; i < P * D; i += kEpThreads) {
-      const int p = i % P, d = i / P;
-      const int h = tl.h0 + p / a.TW, w = tl.w0 + p % a.TW;
+      const int p = i & (P - 1), d = i >> lP;
+      const int h = tl.h0 + (p >> a.lTW), w = tl.w0 + (p & (a.TW - 1));
       float v = 0.f;
       if (h < a.H && w < a.W) {
         const long pos = (long)h * a.W + w;
         v = oy[d * L + pos];
         v = v + oy[2 * ks + d * L + (L - 1 - pos)];
       }
-      sm[p * pitch + d] = v;
+      sm[d * S + (p >> a.lTW) * TW1 + (p & (a.TW - 1))] = v;
     }
     __syncthreads();
     // column-major directions: + y1[w*H + h] + y3[L-1-(w*H + h)]
+#pragma unroll 8
     for (int i = t; i < P * D; i += kEpThreads) {
-      const int q = i % P, d = i / P;
-      const int qh = q % a.TH, qw = q / a.TH;
+      const int q = i & (P - 1), d = i >> lP;
+      const int qh = q & (a.TH - 1), qw = q >> a.lTH;
       const int h = tl.h0 + qh, w = tl.w0 + qw;
       if (h < a.H && w < a.W) {
         const long j = (long)w * a.H + h;
-        float* s = sm + (qh * a.TW + qw) * pitch + d;
-        float v = *s;
-        v = v + oy[ks + d * L + j];
-        v = v + oy[3 * ks + d * L + (L - 1 - j)];
-        *s = v;
+        const float v1 = oy[ks + d * L + j], v3 = oy[3 * ks + d * L + (L - 1 - j)];
+        float* s = sm + d * S + qh * TW1 + qw;
+        *s = (*s + v1) + v3;
       }
     }
     __syncthreads();
-    // LayerNorm over D and the SiLU(z) gate, one warp per position
-    for (int p = warp; p < P; p += kEpThreads / 32) {
-      const int h = tl.h0 + p / a.TW, w = tl.w0 + p % a.TW;
-      if (h >= a.H || w >= a.W) continue;  // warp-uniform
-      const long pos = (long)h * a.W + w;
-      float v[kEpMaxDPL];
-      float s = 0.f;
+    // LayerNorm over D and the SiLU(z) gate: G lanes per position, 8 channels per lane, all z loads issued first
+    float zv[kEpPasses][kEpCPL];
+    long rowv[kEpPasses];
 #pragma unroll
-      for (int i = 0; i < kEpMaxDPL; ++i)
-        if (i < dpl) v[i] = sm[p * pitch + lane + 32 * i], s += v[i];
-      const float mu = warp_sum(s) / (float)D;
+    for (int k = 0; k < kEpPasses; ++k) {
+      const int p = (k * (kEpThreads / 32) + warp) * ppw + lp;
+      const int h = tl.h0 + (p >> a.lTW), w = tl.w0 + (p & (a.TW - 1));
+      const bool ok = p < P && h < a.H && w < a.W;
+      const long pos = ok ? (long)h * a.W + w : 0;
+      rowv[k] = ok ? tl.b * L + pos : -1;
+      ld8<TZ>(zp + tl.b * a.z_bs + pos * a.z_ls + c0, zv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kEpPasses; ++k) {
+      const int p = (k * (kEpThreads / 32) + warp) * ppw + lp;
+      float v[kEpCPL];
+      float s = 0.f;
+      const int slot = (p >> a.lTW) * TW1 + (p & (a.TW - 1));
+#pragma unroll
+      for (int i = 0; i < kEpCPL; ++i) v[i] = sm[(c0 + i) * S + slot], s += v[i];
+      const float mu = group_sum(s, G) * invD;
       float q = 0.f;
 #pragma unroll
-      for (int i = 0; i < kEpMaxDPL; ++i)
-        if (i < dpl) q = fmaf(v[i] - mu, v[i] - mu, q);
-      const float rs = rsqrtf(warp_sum(q) / (float)D + a.eps);
-      const long row = tl.b * L + pos;
-      const TZ* zr = static_cast<const TZ*>(a.z) + tl.b * a.z_bs + pos * a.z_ls;
+      for (int i = 0; i < kEpCPL; ++i) q = fmaf(v[i] - mu, v[i] - mu, q);
+      const float rs = rsqrtf(group_sum(q, G) * invD + a.eps);
+      if (rowv[k] >= 0) {
+        float o[kEpCPL];
 #pragma unroll
-      for (int i = 0; i < kEpMaxDPL; ++i)
-        if (i < dpl) {
-          const int d = lane + 32 * i;
-          const float zz = e_ld<TZ>(zr + d);
-          const float ln = fmaf((v[i] - mu) * rs, gm[i], bt[i]);
-          e_st<TO>(static_cast<TO*>(a.out) + row * D + d, ln * (zz / (1.f + __expf(-zz))));
-          a.ym[row * D + d] = v[i];
+        for (int i = 0; i < kEpCPL; ++i) {
+          const float zz = zv[k][i];
+          o[i] = fmaf((v[i] - mu) * rs, gm[i], bt[i]) * (zz / (1.f + __expf(-zz)));
         }
-      if (lane == 0) a.mean[row] = mu, a.rstd[row] = rs;
+        st8<TO>(outp + rowv[k] * D + c0, o);
+        st8<float>(ymp + rowv[k] * D + c0, v);
+        if (lg == 0) a.mean[rowv[k]] = mu, a.rstd[rowv[k]] = rs;
+      }
     }
     __syncthreads();
   }
@@ -162,73 +223,86 @@ __global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_fwd_kernel(EpArgs a)
 
 template <typename TZ, typename TO, typename TG>
 __global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_bwd_kernel(EpArgs a) {
-  extern __shared__ float sm[];  // [P][D + 1] dy, then [2][D] parameter-gradient fold
-  const int D = a.D, P = a.TH * a.TW, pitch = D + 1;
-  float* red = sm + P * pitch;
+  extern __shared__ float sm[];  // [D][S] dy (layout as in the forward), then [2][D] parameter-gradient fold
+  const int D = a.D, P = a.TH * a.TW, lP = a.lTH + a.lTW, S = (a.TH * (a.TW + 1)) | 1, TW1 = a.TW + 1;
+  float* red = sm + D * S;
   const long L = (long)a.H * a.W;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int dpl = D / 32;
-  float gm[kEpMaxDPL], bt[kEpMaxDPL], ag[kEpMaxDPL], ab[kEpMaxDPL];
+  const int G = D / kEpCPL, ppw = 32 / G;
+  const int lg = lane % G, lp = lane / G;
+  const int c0 = lg * kEpCPL;
+  float gm[kEpCPL], bt[kEpCPL], ag[kEpCPL], ab[kEpCPL];
 #pragma unroll
-  for (int i = 0; i < kEpMaxDPL; ++i) {
+  for (int i = 0; i < kEpCPL; ++i) {
     ag[i] = ab[i] = 0.f;
-    if (i < dpl) gm[i] = a.gamma ? a.gamma[lane + 32 * i] : 1.f, bt[i] = a.beta ? a.beta[lane + 32 * i] : 0.f;
+    gm[i] = a.gamma ? a.gamma[c0 + i] : 1.f, bt[i] = a.beta ? a.beta[c0 + i] : 0.f;
   }
   for (int i = t; i < 2 * D; i += kEpThreads) red[i] = 0.f;
+  const TZ* __restrict__ zp = static_cast<const TZ*>(a.z);
+  const TO* __restrict__ gp = static_cast<const TO*>(a.dout);
+  const float* __restrict__ ymp = a.ym;
+  TZ* __restrict__ dzp = static_cast<TZ*>(a.dz);
+  const float invD = 1.f / (float)D;
   EpTile tl;
   for (long tile = blockIdx.x; ep_tile(a, tile, &tl); tile += gridDim.x) {
     __syncthreads();
-    for (int p = warp; p < P; p += kEpThreads / 32) {
-      const int h = tl.h0 + p / a.TW, w = tl.w0 + p % a.TW;
-      if (h >= a.H || w >= a.W) continue;  // warp-uniform
-      const long pos = (long)h * a.W + w;
+#pragma unroll 2
+    for (int k = 0; k < kEpPasses; ++k) {
+      const int p = (k * (kEpThreads / 32) + warp) * ppw + lp;
+      const int h = tl.h0 + (p >> a.lTW), w = tl.w0 + (p & (a.TW - 1));
+      const bool ok = p < P && h < a.H && w < a.W;
+      const long pos = ok ? (long)h * a.W + w : 0;
       const long row = tl.b * L + pos;
+      float g[kEpCPL], zz[kEpCPL], y[kEpCPL];
+      ld8<TO>(gp + row * D + c0, g);
+      ld8<TZ>(zp + tl.b * a.z_bs + pos * a.z_ls + c0, zz);
+      ld8<float>(ymp + row * D + c0, y);
       const float mu = a.mean[row], rs = a.rstd[row];
-      const TZ* zr = static_cast<const TZ*>(a.z) + tl.b * a.z_bs + pos * a.z_ls;
-      float xh[kEpMaxDPL], gg[kEpMaxDPL];
+      float xh[kEpCPL], gg[kEpCPL], dzv[kEpCPL];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < kEpMaxDPL; ++i)
-        if (i < dpl) {
-          const int d = lane + 32 * i;
-          const float g = e_ld<TO>(static_cast<const TO*>(a.dout) + row * D + d);
-          const float zz = e_ld<TZ>(zr + d);
-          const float sg = 1.f / (1.f + __expf(-zz));
-          xh[i] = (a.ym[row * D + d] - mu) * rs;
-          const float ln = fmaf(xh[i], gm[i], bt[i]);
-          e_st<TZ>(static_cast<TZ*>(a.dz) + row * D + d, g * ln * sg * (1.f + zz * (1.f - sg)));
-          const float dln = g * zz * sg;
-          ag[i] = fmaf(dln, xh[i], ag[i]);
-          ab[i] += dln;
-          gg[i] = dln * gm[i];
-          s1 += gg[i];
-          s2 = fmaf(gg[i], xh[i], s2);
-        }
-      const float m1 = warp_sum(s1) / (float)D, m2 = warp_sum(s2) / (float)D;
+      for (int i = 0; i < kEpCPL; ++i) {
+        const float sg = 1.f / (1.f + __expf(-zz[i]));
+        xh[i] = (y[i] - mu) * rs;
+        const float ln = fmaf(xh[i], gm[i], bt[i]);
+        dzv[i] = g[i] * ln * sg * (1.f + zz[i] * (1.f - sg));
+        const float dln = ok ? g[i] * zz[i] * sg : 0.f;
+        ag[i] = fmaf(dln, xh[i], ag[i]);
+        ab[i] += dln;
+        gg[i] = dln * gm[i];
+        s1 += gg[i];
+        s2 = fmaf(gg[i], xh[i], s2);
+      }
+      const float m1 = group_sum(s1, G) * invD, m2 = group_sum(s2, G) * invD;
+      if (ok) st8<TZ>(dzp + row * D + c0, dzv);
+      {
+        const int slot = (p >> a.lTW) * TW1 + (p & (a.TW - 1));
 #pragma unroll
-      for (int i = 0; i < kEpMaxDPL; ++i)
-        if (i < dpl) sm[p * pitch + lane + 32 * i] = rs * (gg[i] - m1 - xh[i] * m2);
+        for (int i = 0; i < kEpCPL; ++i) sm[(c0 + i) * S + slot] = rs * (gg[i] - m1 - xh[i] * m2);
+      }
     }
     __syncthreads();
-    TG* go = static_cast<TG*>(a.d_out_y) + tl.b * 4 * D * L;
+    TG* __restrict__ go = static_cast<TG*>(a.d_out_y) + tl.b * 4 * D * L;
     const long ks = (long)D * L;
+#pragma unroll 8
     for (int i = t; i < P * D; i += kEpThreads) {  // row-major copies
-      const int p = i % P, d = i / P;
-      const int h = tl.h0 + p / a.TW, w = tl.w0 + p % a.TW;
+      const int p = i & (P - 1), d = i >> lP;
+      const int h = tl.h0 + (p >> a.lTW), w = tl.w0 + (p & (a.TW - 1));
       if (h < a.H && w < a.W) {
         const long pos = (long)h * a.W + w;
-        const float v = sm[p * pitch + d];
+        const float v = sm[d * S + (p >> a.lTW) * TW1 + (p & (a.TW - 1))];
         e_st<TG>(go + d * L + pos, v);
         e_st<TG>(go + 2 * ks + d * L + (L - 1 - pos), v);
       }
     }
+#pragma unroll 8
     for (int i = t; i < P * D; i += kEpThreads) {  // column-major copies
-      const int q = i % P, d = i / P;
-      const int qh = q % a.TH, qw = q / a.TH;
+      const int q = i & (P - 1), d = i >> lP;
+      const int qh = q & (a.TH - 1), qw = q >> a.lTH;
       const int h = tl.h0 + qh, w = tl.w0 + qw;
       if (h < a.H && w < a.W) {
         const long j = (long)w * a.H + h;
-        const float v = sm[(qh * a.TW + qw) * pitch + d];
+        const float v = sm[d * S + qh * TW1 + qw];
         e_st<TG>(go + ks + d * L + j, v);
         e_st<TG>(go + 3 * ks + d * L + (L - 1 - j), v);
       }
@@ -236,11 +310,10 @@ __global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_bwd_kernel(EpArgs a)
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < kEpMaxDPL; ++i)
-    if (i < dpl) {
-      atomicAdd(red + lane + 32 * i, ag[i]);
-      atomicAdd(red + D + lane + 32 * i, ab[i]);
-    }
+  for (int i = 0; i < kEpCPL; ++i) {
+    atomicAdd(red + c0 + i, ag[i]);
+    atomicAdd(red + D + c0 + i, ab[i]);
+  }
   __syncthreads();
   for (int i = t; i < D; i += kEpThreads) {
     if (a.dgamma) atomicAdd(a.dgamma + i, red[i]);
@@ -248,14 +321,19 @@ __global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_bwd_kernel(EpArgs a)
   }
 }
 
+static bool ep_supported(int D) { return D == 32 || D == 64 || D == 128 || D == 256; }
+
 static bool ep_config(EpArgs& a, size_t* smem, int* grid, bool bwd) {
-  if (a.D % 32 || a.D < 32 || a.D > 32 * kEpMaxDPL) return false;
+  if (!ep_supported(a.D)) return false;
   // positions per tile so that the tile stays near 32 KB: 256 / 128 / 64 / 32 for D = 32 / 64 / 128 / 256
-  int P = 8192 / a.D;
-  if (P > 256) P = 256;
-  a.TW = P >= 256 ? 16 : (P >= 128 ? 16 : 8);
-  a.TH = P / a.TW;
-  *smem = ((size_t)P * (a.D + 1) + (bwd ? 2 * a.D : 0)) * sizeof(float);
+  int lP = 8;
+  while ((1 << lP) * a.D > 8192) --lP;  // 256 positions at D = 32 ... 32 at D = 256
+  const int P = 1 << lP;
+  a.lTW = lP >= 7 ? 4 : 3;
+  a.lTH = lP - a.lTW;
+  a.TW = 1 << a.lTW, a.TH = 1 << a.lTH;
+  (void)P;
+  *smem = ((size_t)a.D * ((a.TH * (a.TW + 1)) | 1) + (bwd ? 2 * a.D : 0)) * sizeof(float);
   const long tiles = (long)a.B * ((a.W + a.TW - 1) / a.TW) * ((a.H + a.TH - 1) / a.TH);
   *grid = (int)(tiles < 148L * 8 ? tiles : 148L * 8);
   return true;
@@ -263,7 +341,7 @@ static bool ep_config(EpArgs& a, size_t* smem, int* grid, bool bwd) {
 
 }  // namespace nz
 
-extern "C" int nz_ss2d_epilogue_supported(int32_t D) { return (D % 32 == 0 && D >= 32 && D <= 32 * nz::kEpMaxDPL) ? 1 : 0; }
+extern "C" int nz_ss2d_epilogue_supported(int32_t D) { return nz::ep_supported(D) ? 1 : 0; }
 
 extern "C" int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma,
                                     const float* beta, void* out, float* y_merged, float* mean, float* rstd,
@@ -280,7 +358,7 @@ extern "C" int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int
   size_t smem;
   int grid;
   if (!ep_config(a, &smem, &grid, false)) {
-    set_error("nz_ss2d_epilogue_fwd: D = %d unsupported (multiple of 32, 32..256)", D);
+    set_error("nz_ss2d_epilogue_fwd: D = %d unsupported (32, 64, 128 or 256)", D);
     return NZ_EUNSUPPORTED;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -323,7 +401,7 @@ extern "C" int nz_ss2d_epilogue_bwd(const void* dout, const float* y_merged, con
   size_t smem;
   int grid;
   if (!ep_config(a, &smem, &grid, true)) {
-    set_error("nz_ss2d_epilogue_bwd: D = %d unsupported (multiple of 32, 32..256)", D);
+    set_error("nz_ss2d_epilogue_bwd: D = %d unsupported (32, 64, 128 or 256)", D);
     return NZ_EUNSUPPORTED;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
