@@ -132,7 +132,7 @@ __device__ __forceinline__ bool ep_tile(const EpArgs& a, long tile, EpTile* t) {
 }
 
 template <typename TZ, typename TO>
-__global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_fwd_kernel(EpArgs a) {
+__global__ void __launch_bounds__(kEpThreads, 4) ss2d_epilogue_fwd_kernel(EpArgs a) {
   extern __shared__ float sm[];  // [D][S], S = TH * (TW + 1) made odd: position (ph, pw) sits at ph * (TW + 1) + pw
   const int D = a.D, P = a.TH * a.TW, lP = a.lTH + a.lTW, S = (a.TH * (a.TW + 1)) | 1, TW1 = a.TW + 1;
   const long L = (long)a.H * a.W;
@@ -180,41 +180,45 @@ __global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_fwd_kernel(EpArgs a)
       }
     }
     __syncthreads();
-    // LayerNorm over D and the SiLU(z) gate: G lanes per position, 8 channels per lane, all z loads issued first
-    float zv[kEpPasses][kEpCPL];
-    long rowv[kEpPasses];
+    // LayerNorm over D and the SiLU(z) gate: G lanes per position, 8 channels per lane; the z vectors of two passes
+    // are requested before the first of them is used
 #pragma unroll
-    for (int k = 0; k < kEpPasses; ++k) {
-      const int p = (k * (kEpThreads / 32) + warp) * ppw + lp;
-      const int h = tl.h0 + (p >> a.lTW), w = tl.w0 + (p & (a.TW - 1));
-      const bool ok = p < P && h < a.H && w < a.W;
-      const long pos = ok ? (long)h * a.W + w : 0;
-      rowv[k] = ok ? tl.b * L + pos : -1;
-      ld8<TZ>(zp + tl.b * a.z_bs + pos * a.z_ls + c0, zv[k]);
-    }
+    for (int k0 = 0; k0 < kEpPasses; k0 += 2) {
+      float zv[2][kEpCPL];
+      long rowv[2];
 #pragma unroll
-    for (int k = 0; k < kEpPasses; ++k) {
-      const int p = (k * (kEpThreads / 32) + warp) * ppw + lp;
-      float v[kEpCPL];
-      float s = 0.f;
-      const int slot = (p >> a.lTW) * TW1 + (p & (a.TW - 1));
+      for (int kk = 0; kk < 2; ++kk) {
+        const int p = ((k0 + kk) * (kEpThreads / 32) + warp) * ppw + lp;
+        const int h = tl.h0 + (p >> a.lTW), w = tl.w0 + (p & (a.TW - 1));
+        const bool ok = h < a.H && w < a.W;
+        const long pos = ok ? (long)h * a.W + w : 0;
+        rowv[kk] = ok ? tl.b * L + pos : -1;
+        ld8<TZ>(zp + tl.b * a.z_bs + pos * a.z_ls + c0, zv[kk]);
+      }
 #pragma unroll
-      for (int i = 0; i < kEpCPL; ++i) v[i] = sm[(c0 + i) * S + slot], s += v[i];
-      const float mu = group_sum(s, G) * invD;
-      float q = 0.f;
+      for (int kk = 0; kk < 2; ++kk) {
+        const int p = ((k0 + kk) * (kEpThreads / 32) + warp) * ppw + lp;
+        float v[kEpCPL];
+        float s = 0.f;
+        const int slot = (p >> a.lTW) * TW1 + (p & (a.TW - 1));
 #pragma unroll
-      for (int i = 0; i < kEpCPL; ++i) q = fmaf(v[i] - mu, v[i] - mu, q);
-      const float rs = rsqrtf(group_sum(q, G) * invD + a.eps);
-      if (rowv[k] >= 0) {
-        float o[kEpCPL];
+        for (int i = 0; i < kEpCPL; ++i) v[i] = sm[(c0 + i) * S + slot], s += v[i];
+        const float mu = group_sum(s, G) * invD;
+        float q = 0.f;
 #pragma unroll
-        for (int i = 0; i < kEpCPL; ++i) {
-          const float zz = zv[k][i];
-          o[i] = fmaf((v[i] - mu) * rs, gm[i], bt[i]) * (zz / (1.f + __expf(-zz)));
+        for (int i = 0; i < kEpCPL; ++i) q = fmaf(v[i] - mu, v[i] - mu, q);
+        const float rs = rsqrtf(group_sum(q, G) * invD + a.eps);
+        if (rowv[kk] >= 0) {
+          float o[kEpCPL];
+#pragma unroll
+          for (int i = 0; i < kEpCPL; ++i) {
+            const float zz = zv[kk][i];
+            o[i] = fmaf((v[i] - mu) * rs, gm[i], bt[i]) * (zz / (1.f + __expf(-zz)));
+          }
+          st8<TO>(outp + rowv[kk] * D + c0, o);
+          st8<float>(ymp + rowv[kk] * D + c0, v);
+          if (lg == 0) a.mean[rowv[kk]] = mu, a.rstd[rowv[kk]] = rs;
         }
-        st8<TO>(outp + rowv[k] * D + c0, o);
-        st8<float>(ymp + rowv[k] * D + c0, v);
-        if (lg == 0) a.mean[rowv[k]] = mu, a.rstd[rowv[k]] = rs;
       }
     }
     __syncthreads();
@@ -222,7 +226,7 @@ __global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_fwd_kernel(EpArgs a)
 }
 
 template <typename TZ, typename TO, typename TG>
-__global__ void __launch_bounds__(kEpThreads) ss2d_epilogue_bwd_kernel(EpArgs a) {
+__global__ void __launch_bounds__(kEpThreads, 3) ss2d_epilogue_bwd_kernel(EpArgs a) {
   extern __shared__ float sm[];  // [D][S] dy (layout as in the forward), then [2][D] parameter-gradient fold
   const int D = a.D, P = a.TH * a.TW, lP = a.lTH + a.lTW, S = (a.TH * (a.TW + 1)) | 1, TW1 = a.TW + 1;
   float* red = sm + D * S;
