@@ -6,10 +6,11 @@
 // The op is HBM-bound: forward reads x and writes y once; backward reads x and dy and writes dx once.
 //
 // Forward: a thread owns one column and kRows consecutive rows of a plane and slides a 3x3 window down
-// (3 loads per new row, neighbours' loads hit L1).  Backward: a CTA owns a kTH x kTW tile; it first recomputes the
-// pre-activation (from x staged in shared memory with a two-pixel ring) on the tile plus a one-pixel ring and stores dpre = dy * silu'(pre) in shared memory, then every
-// thread forms dx (the transposed stencil over dpre) and its share of dweight[3][3] / dbias, which are reduced over
-// the CTA (warp shuffles + shared memory) and flushed with 10 atomicAdds per CTA (caller zeroes them).
+// (3 loads per new row, neighbours' loads hit L1).  Backward: a CTA owns a kTH x kTW tile; it stages x with a two-pixel
+// ring in shared memory, recomputes the pre-activation on the tile plus a one-pixel ring and stores
+// dpre = dy * silu'(pre) in shared memory, then every thread forms dx (the transposed stencil over dpre) and its share of
+// dweight[3][3] / dbias, which are reduced over the CTA (warp shuffles + shared memory) and flushed with 10 atomicAdds
+// per CTA (caller zeroes them).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
