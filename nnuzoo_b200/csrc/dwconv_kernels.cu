@@ -94,7 +94,90 @@ __global__ void __launch_bounds__(256) dwconv3x3_silu_fwd_kernel(const T* __rest
   }
 }
 
-constexpr int kTH = 8, kTW = 64;  // backward tile (interior); 256 threads, 2 interior pixels per thread
+
+// 8 consecutive elements -> 8 floats / back (one 16-byte access for 16-bit types, two for fp32)
+template <typename T>
+__device__ __forceinline__ void ld8g(const T* __restrict__ p, float* f) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w, f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+  } else {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = ld_f32<T>(e + i);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st8g(T* __restrict__ p, const float* f) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+  } else {
+    uint4 v;
+    T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) st_f32<T>(e + i, f[i]);
+    *reinterpret_cast<uint4*>(p) = v;
+  }
+}
+
+// forward, W % 8 == 0 and 16-byte aligned planes: a thread owns 8 columns x kRows rows; per row one vector load plus
+// the two neighbours' edge elements
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv3x3_silu_fwd_vec_kernel(const T* __restrict__ x,
+                                                                     const float* __restrict__ wgt,
+                                                                     const float* __restrict__ bias, T* __restrict__ y,
+                                                                     long planes, int dim, int H, int W, int silu) {
+  const int strips = (H + kRows - 1) / kRows, W8 = W / 8;
+  const long total = planes * strips * W8;
+  for (long i = blockIdx.x * 256L + threadIdx.x; i < total; i += (long)gridDim.x * 256) {
+    const int w0 = (int)(i % W8) * 8;
+    const int strip = (int)((i / W8) % strips);
+    const long plane = i / ((long)W8 * strips);
+    const int d = (int)(plane % dim);
+    float k[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) k[q] = wgt[d * 9 + q];
+    const float b = bias ? bias[d] : 0.f;
+    const T* xp = x + plane * (long)H * W;
+    T* yp = y + plane * (long)H * W;
+    const int h0 = strip * kRows;
+    float r0[10], r1[10], r2[10];
+    auto load_row = [&](int h, float* r) {
+      if (h < 0 || h >= H) {
+#pragma unroll
+        for (int c = 0; c < 10; ++c) r[c] = 0.f;
+      } else {
+        const T* p = xp + (long)h * W + w0;
+        ld8g<T>(p, r + 1);
+        r[0] = w0 > 0 ? ld_f32<T>(p - 1) : 0.f;
+        r[9] = w0 + 8 < W ? ld_f32<T>(p + 8) : 0.f;
+      }
+    };
+    load_row(h0 - 1, r0);
+    load_row(h0, r1);
+#pragma unroll
+    for (int j = 0; j < kRows; ++j) {
+      const int h = h0 + j;
+      if (h >= H) break;
+      load_row(h + 1, r2);
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float acc = b;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) acc = fmaf(k[q], r0[c + q], fmaf(k[3 + q], r1[c + q], fmaf(k[6 + q], r2[c + q], acc)));
+        o[c] = silu ? silu_f(acc) : acc;
+      }
+      st8g<T>(yp + (long)h * W + w0, o);
+#pragma unroll
+      for (int c = 0; c < 10; ++c) r0[c] = r1[c], r1[c] = r2[c];
+    }
+  }
+}
+
+constexpr int kTH = 32, kTW = 64;  // backward tile (interior); 256 threads, 8 interior pixels per thread between barriers
 
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv3x3_silu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy,
@@ -214,8 +297,23 @@ extern "C" int nz_dwconv3x3_fwd(const void* x, const float* weight, const float*
     return NZ_EINVAL;
   }
   const long planes = (long)batch * dim;
-  const int grid = grid_for(planes * ((H + kRows - 1) / kRows) * W);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (W % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 &&
+      (dtype == NZ_F32 || dtype == NZ_BF16 || dtype == NZ_F16)) {
+    const int gridv = grid_for(planes * ((H + kRows - 1) / kRows) * (W / 8));
+    if (dtype == NZ_F32)
+      dwconv3x3_silu_fwd_vec_kernel<float><<<gridv, 256, 0, st>>>(static_cast<const float*>(x), weight, bias,
+                                                                  static_cast<float*>(y), planes, dim, H, W, silu);
+    else if (dtype == NZ_BF16)
+      dwconv3x3_silu_fwd_vec_kernel<__nv_bfloat16><<<gridv, 256, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(x), weight, bias, static_cast<__nv_bfloat16*>(y), planes, dim, H, W, silu);
+    else
+      dwconv3x3_silu_fwd_vec_kernel<__half><<<gridv, 256, 0, st>>>(static_cast<const __half*>(x), weight, bias,
+                                                                   static_cast<__half*>(y), planes, dim, H, W, silu);
+    count_launch(1);
+    return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+  }
+  const int grid = grid_for(planes * ((H + kRows - 1) / kRows) * W);
   if (dtype == NZ_F32)
     dwconv3x3_silu_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), weight, bias,
                                                            static_cast<float*>(y), planes, dim, H, W, silu);
