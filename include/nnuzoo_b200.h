@@ -115,6 +115,12 @@ typedef struct NzScanDesc {
 /* Bytes of scratch a call with this batch / dim needs (same for forward and backward). */
 int64_t nz_scan_workspace_bytes(const NzScanDesc* desc);
 
+/* Optional larger scratch size: for launches with far fewer row blocks than SMs and many chunks (the 1-D nets'
+ * (2, 64, 2 M) scans, batch-1 inference) nz_scan_fwd runs chunk-parallel -- aggregate pass, combine, final pass -- instead
+ * of handing the state from chunk to chunk, provided `workspace_bytes` >= this value (else it uses the chained scheme).
+ * Equals nz_scan_workspace_bytes() for every other shape.  Results are bit-identical either way. */
+int64_t nz_scan_workspace_bytes_cp(const NzScanDesc* desc);
+
 /* Number of NZ_CHUNK-long chunks (second-to-last extent of the checkpoint tensor x). */
 int64_t nz_scan_num_chunks(int64_t seqlen);
 

@@ -80,6 +80,8 @@ def lib():
                 L.nz_scan_num_chunks.restype = _i64
                 L.nz_scan_workspace_bytes.argtypes = [ctypes.POINTER(NzScanDesc)]
                 L.nz_scan_workspace_bytes.restype = _i64
+                L.nz_scan_workspace_bytes_cp.argtypes = [ctypes.POINTER(NzScanDesc)]
+                L.nz_scan_workspace_bytes_cp.restype = _i64
                 for name in ("nz_scan_fwd", "nz_scan_bwd", "nz_scan_fwd_bwd_host"):
                     fn = getattr(L, name)
                     fn.argtypes = [ctypes.POINTER(NzScanDesc), _vp]

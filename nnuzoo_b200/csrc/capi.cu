@@ -206,6 +206,73 @@ static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   return ok;
 }
 
+// ---- chunk-parallel forward (few rows, long L) --------------------------------------------------------------
+// The chained hand-off serialises the chunks of a row block; with fewer row blocks than SMs that chain is all there
+// is (BASELINE configs[2]: 128 rows x 2 M steps = 8 row blocks x 8192 links, 1.9 % of the HBM peak).  When the caller
+// provides the larger workspace of nz_scan_workspace_bytes_cp(), the forward runs as three launches instead:
+// aggregate pass (all tiles at once, h = 0 in, (prod a, h_end) out), a combine kernel that walks the chunks of every
+// (row, state) -- h_in[c+1] = fma(P_c, h_in[c], H_c), the very operation the chained kernel performs, so the results are
+// bit-identical -- and the final pass with every tile on the fast path.
+static bool cp_eligible(const NzScanDesc* d) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int dpg = d->dim / (d->ngroups > 0 ? d->ngroups : 1);
+  const long nrb_total = (long)d->batch * d->ngroups * ((dpg + kFwdRows - 1) / kFwdRows);
+  const long nchunks = (d->seqlen + kFwdTL - 1) / kFwdTL;
+  if (getenv("NZ_NO_CP")) return false;
+  return nrb_total <= sms / 2 && nchunks >= 16;
+}
+static int64_t cp_extra_bytes(const NzScanDesc* d) {
+  const int64_t nchunks = (d->seqlen + kFwdTL - 1) / kFwdTL;
+  return 3 * (int64_t)d->batch * d->dim * NZ_MAX_DSTATE * nchunks * (int64_t)sizeof(float);
+}
+
+__global__ void __launch_bounds__(128) cp_combine_kernel(const float* __restrict__ P, const float* __restrict__ H,
+                                                         float* __restrict__ hin, long nseq, int nchunks) {
+  const long s = blockIdx.x * 128L + threadIdx.x;  // one (row, state) sequence of chunk aggregates per thread
+  if (s >= nseq) return;
+  const float* p = P + s * nchunks;
+  const float* g = H + s * nchunks;
+  float* o = hin + s * nchunks;
+  float h = 0.f;
+  int c = 0;
+  for (; c + 16 <= nchunks; c += 16) {  // 32 independent loads in flight, then the serial chain
+    float pv[16], gv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pv[i] = p[c + i], gv[i] = g[c + i];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      o[c + i] = h;
+      h = fmaf(pv[i], h, gv[i]);
+    }
+  }
+  for (; c < nchunks; ++c) {
+    o[c] = h;
+    h = fmaf(p[c], h, g[c]);
+  }
+}
+
+template <typename T>
+static cudaError_t run_fwd_cp(ScanKArgs a, const NzScanDesc* d, bool tma, bool has_z, cudaStream_t st) {
+  float* base = reinterpret_cast<float*>(reinterpret_cast<char*>(d->workspace) + nz_scan_workspace_bytes(d));
+  const long nseq = (long)d->batch * d->dim * NZ_MAX_DSTATE;
+  a.cp_P = base;
+  a.cp_H = base + nseq * a.nchunks;
+  float* hin = base + 2 * nseq * a.nchunks;
+  a.cp_hin = hin;
+  a.claim_late = 0;  // the tiles are independent in both passes
+  a.cp_mode = 1;
+  cudaError_t e = launch_scan_fwd<T>(a, tma, has_z, st);
+  if (e != cudaSuccess) return e;
+  cp_combine_kernel<<<(unsigned)((nseq + 127) / 128), 128, 0, st>>>(a.cp_P, a.cp_H, hin, nseq, a.nchunks);
+  e = cudaMemsetAsync(d->workspace, 0, kWsHeader, st);  // the ticket counter starts over
+  if (e != cudaSuccess) return e;
+  a.cp_mode = 2;
+  e = launch_scan_fwd<T>(a, tma, has_z, st);
+  if (e == cudaSuccess) count_launch(2);
+  return e;
+}
+
 static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   int rc = validate(d, bwd);
   if (rc) return rc;
@@ -217,7 +284,12 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaMemsetAsync(d->workspace, 0, (size_t)nz_scan_workspace_bytes(d), st);
   if (e != cudaSuccess) return fail(NZ_ECUDA, "workspace memset failed: %s", cudaGetErrorString(e));
-  if (d->dtype == NZ_F32)
+  const bool cp = !bwd && cp_eligible(d) && d->workspace_bytes >= nz_scan_workspace_bytes_cp(d);
+  if (cp) {
+    if (d->dtype == NZ_F32) e = run_fwd_cp<float>(a, d, tma, has_z, st);
+    else if (d->dtype == NZ_BF16) e = run_fwd_cp<__nv_bfloat16>(a, d, tma, has_z, st);
+    else e = run_fwd_cp<__half>(a, d, tma, has_z, st);
+  } else if (d->dtype == NZ_F32)
     e = bwd ? launch_scan_bwd<float>(a, tma, has_z, st) : launch_scan_fwd<float>(a, tma, has_z, st);
   else if (d->dtype == NZ_BF16)
     e = bwd ? launch_scan_bwd<__nv_bfloat16>(a, tma, has_z, st) : launch_scan_fwd<__nv_bfloat16>(a, tma, has_z, st);
@@ -239,6 +311,12 @@ int64_t nz_scan_workspace_bytes(const NzScanDesc* d) {
   if (!d || d->batch < 1 || d->dim < 1) return 0;
   // ticket header + per (batch, dim) row: 2 ring slots x 16 states x {fp32 value, u32 tag}
   return (int64_t)nz::kWsHeader + (int64_t)d->batch * d->dim * 2 * NZ_MAX_DSTATE * 8;
+}
+
+int64_t nz_scan_workspace_bytes_cp(const NzScanDesc* d) {
+  const int64_t base = nz_scan_workspace_bytes(d);
+  if (base == 0 || d->ngroups < 1 || d->seqlen < 1 || d->dim % d->ngroups) return base;
+  return nz::cp_eligible(d) ? base + nz::cp_extra_bytes(d) : base;
 }
 
 int nz_scan_fwd(const NzScanDesc* desc, void* stream) { return nz::run_scan(desc, stream, false); }

@@ -95,6 +95,13 @@ struct alignas(64) ScanKArgs {
   int skew;      // states the later chunk's tile must be ahead before a dependent tile starts polling
   int vec_out;   // out rows 16-byte aligned -> vector stores
   int out_f32;   // 16-bit instantiations only: `out` is fp32 (NzScanDesc::out_f32)
+  // chunk-parallel forward for few-rows / long-L launches (capi.cu: run_scan_fwd_cp).  0: chained hand-off (default);
+  // 1: aggregate pass -- every tile starts from h = 0, publishes its (prod a, h_end) per (row, state) and skips the
+  // replay / read-out; 2: final pass -- the carries come from cp_hin, nothing is polled or published.
+  // Arrays are [row][state][chunk] fp32.
+  int cp_mode;
+  float *cp_P, *cp_H;
+  const float* cp_hin;
   int vec_grad;  // du/ddelta/dz and dB/dC rows 16-byte aligned
 };
 
@@ -383,13 +390,17 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
       a2pre[j] = ok ? __ldg(a.A + (long)(q.d0 + r) * a.A_ds + n) * kLog2e : 0.f;
       hpre[j] = 0.f;
       if (ok && c > 0) {
-        unsigned tag;
-        slot_load(a.carry + ((((long)q.b * a.dim + q.d0 + r) * 2 + ((c - 1) & 1)) * kMaxState + n), hpre[j], tag);
-        all_in = all_in && tag == (unsigned)c;
+        if (a.cp_mode == 0) {
+          unsigned tag;
+          slot_load(a.carry + ((((long)q.b * a.dim + q.d0 + r) * 2 + ((c - 1) & 1)) * kMaxState + n), hpre[j], tag);
+          all_in = all_in && tag == (unsigned)c;
+        } else if (a.cp_mode == 2) {
+          hpre[j] = __ldg(a.cp_hin + (((long)q.b * a.dim + q.d0 + r) * kMaxState + n) * a.nchunks + c);
+        }
       }
     }
     const unsigned long long* cin = a.carry + (rowg * 2 + ((c - 1) & 1)) * kMaxState;
-    const bool chained = c > 0 && row_ok;
+    const bool chained = c > 0 && row_ok && a.cp_mode == 0;
     bool fast;  // every h carry of the tile was already there: no polling in the state loop
 
     if constexpr (kTMA) {
@@ -588,9 +599,18 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
       for (int qi = 0; qi < NQ; ++qi) {
         h[qi] = ks_enter_up_w<RPW>(P[qi], H[qi], hc[qi]);
         const float hend = fmaf(P[qi], hc[qi], H[qi]);  // state at the end of this lane's segment
-        if (sl == LPR - 1 && row_ok) slot_store(const_cast<unsigned long long*>(cin_p) + coff + qi, hend, (unsigned)c + 1u);
-        if (ck_lane && n + qi < N) x_p[qi] = hend;
+        if (sl == LPR - 1 && row_ok) {
+          if (a.cp_mode == 0) {
+            slot_store(const_cast<unsigned long long*>(cin_p) + coff + qi, hend, (unsigned)c + 1u);
+          } else if (a.cp_mode == 1 && n + qi < N) {
+            const long ix = (rowg * kMaxState + n + qi) * a.nchunks + c;
+            a.cp_P[ix] = P[qi];   // inclusive aggregate of the last segment = the whole tile
+            a.cp_H[ix] = H[qi];
+          }
+        }
+        if (ck_lane && n + qi < N && a.cp_mode != 1) x_p[qi] = hend;
       }
+      if (a.cp_mode == 1) continue;  // aggregate pass: no replay, no read-out
 #if NZ_FWD_SPLIT
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) Ha[qi] = fmaf(Pa[qi], h[qi], Ha[qi]);  // state in the middle of the segment
@@ -631,7 +651,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
 #pragma unroll
       for (int i = 0; i < M; ++i) y[i] *= zz[i] * sigmoid_f(zz[i]);
     }
-    if (row_ok) {
+    if (row_ok && a.cp_mode != 1) {
       if (sizeof(T) == 2 && a.out_f32)
         stg_items<float, M>(reinterpret_cast<float*>(a.out) + (long)q.b * a.o_bs + (long)d * a.o_ds, y, t0, a.L,
                             a.vec_out != 0);

@@ -72,7 +72,8 @@ def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, forc
     desc.A_stride = A.stride(0)
     # scratch for the tile tickets and the chained state hand-off; the call zeroes it on the stream.
     # (the caching allocator orders its reuse after this stream's launches)
-    nbytes = _native.workspace_bytes(batch, dim)
+    # (the _cp size lets few-rows / long-L forwards run chunk-parallel; it equals the base size for other shapes)
+    nbytes = max(_native.workspace_bytes(batch, dim), int(_native.lib().nz_scan_workspace_bytes_cp(ctypes.byref(desc))))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=u.device)
     desc.workspace, desc.workspace_bytes = _ptr(ws), nbytes
     return ws

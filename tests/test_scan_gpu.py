@@ -316,3 +316,39 @@ def test_16bit_operands_fp32_result_equals_widened_fp32_scan(dtype):
     assert rel_err(o_mix.cpu().numpy(), o_ref.cpu().numpy()) < 1e-5
     for a, b in zip(g_mix, g_ref):
         assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [(1, 64, 1, 10240, torch.bfloat16, True), (2, 32, 2, 4196, torch.float32, False),
+                                  (1, 128, 4, 65536, torch.float32, False), (2, 48, 1, 5000, torch.float16, True)])
+def test_chunk_parallel_forward_is_bit_identical_to_the_chained_one(case, monkeypatch):
+    """Few row blocks + many chunks: nz_scan_fwd runs aggregate pass / combine / final pass (capi.cu run_fwd_cp) when the
+    workspace has the _cp size.  The combine performs the chained kernel's own fma per link, so out, the checkpoints
+    (hence every gradient) and last_state must be IDENTICAL to the chained run (NZ_NO_CP=1)."""
+    from nnuzoo_b200 import _native, selective_scan_fn
+    Bn, D, G, L, dtype, has_z = case
+    torch.manual_seed(L)
+    mk = lambda *s: torch.randn(*s, device="cuda")  # noqa: E731
+    u, dl = mk(Bn, D, L).to(dtype), (0.5 * mk(Bn, D, L)).to(dtype)
+    z = mk(Bn, D, L).to(dtype) if has_z else None
+    Bm, Cm = mk(Bn, G, 16, L).to(dtype), mk(Bn, G, 16, L).to(dtype)
+    A = -torch.exp(0.3 * mk(D, 16)) * torch.arange(1, 17, device="cuda")
+    Dp, bias = mk(D), -2 + 0.3 * mk(D)
+    gout = mk(Bn, D, L).to(dtype)
+
+    def run():
+        leaves = [t.detach().clone().requires_grad_(True) for t in (u, dl, Bm, Cm, A, Dp, bias)]
+        n0 = _native.launch_count()
+        out, last = selective_scan_fn(leaves[0], leaves[1], leaves[4], leaves[2], leaves[3], leaves[5], z, leaves[6],
+                                      True, True)
+        launches = _native.launch_count() - n0
+        out.backward(gout)
+        return out.detach(), last.detach(), [t.grad for t in leaves], launches
+
+    o_cp, l_cp, g_cp, n_cp = run()
+    monkeypatch.setenv("NZ_NO_CP", "1")
+    o_ch, l_ch, g_ch, n_ch = run()
+    assert (n_cp, n_ch) == (3, 1), "the chunk-parallel path must actually have been taken"
+    assert torch.equal(o_cp, o_ch) and torch.equal(l_cp, l_ch)
+    for a, b in zip(g_cp, g_ch):
+        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < 1e-6   # (atomics order differs run to run)
