@@ -53,7 +53,7 @@ def _check_inputs(u, delta, A, B, C, D, z, delta_bias):
         raise NotImplementedError(f"d_state {A.shape[1]} > {_native.NZ_MAX_DSTATE} is not implemented")
 
 
-def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, force_generic):
+def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, force_generic, forward=False):
     batch, dim, L = u.shape
     desc.batch, desc.dim, desc.dstate, desc.ngroups = batch, dim, A.shape[1], B.shape[1]
     desc.seqlen = L
@@ -73,7 +73,9 @@ def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, forc
     # scratch for the tile tickets and the chained state hand-off; the call zeroes it on the stream.
     # (the caching allocator orders its reuse after this stream's launches)
     # (the _cp size lets few-rows / long-L forwards run chunk-parallel; it equals the base size for other shapes)
-    nbytes = max(_native.workspace_bytes(batch, dim), int(_native.lib().nz_scan_workspace_bytes_cp(ctypes.byref(desc))))
+    nbytes = _native.workspace_bytes(batch, dim)
+    if forward and L >= 4096:
+        nbytes = max(nbytes, int(_native.lib().nz_scan_workspace_bytes_cp(ctypes.byref(desc))))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=u.device)
     desc.workspace, desc.workspace_bytes = _ptr(ws), nbytes
     return ws
@@ -131,7 +133,7 @@ class SelectiveScanFn(torch.autograd.Function):
         out = torch.empty((batch, dim, L), dtype=torch.float32 if out_f32 else u.dtype, device=u.device)
         x = torch.empty((batch, dim, nchunks, N), dtype=torch.float32, device=u.device)
         desc = NzScanDesc()
-        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC)
+        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC, forward=True)
         desc.out_f32 = int(out_f32)
         desc.out = _ptr(out)
         desc.out_stride[0], desc.out_stride[1] = out.stride(0), out.stride(1)

@@ -350,5 +350,6 @@ def test_chunk_parallel_forward_is_bit_identical_to_the_chained_one(case, monkey
     o_ch, l_ch, g_ch, n_ch = run()
     assert (n_cp, n_ch) == (3, 1), "the chunk-parallel path must actually have been taken"
     assert torch.equal(o_cp, o_ch) and torch.equal(l_cp, l_ch)
-    for a, b in zip(g_cp, g_ch):
-        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < 1e-6   # (atomics order differs run to run)
+    for a, b in zip(g_cp, g_ch):   # same checkpoints -> same gradients up to the run-to-run order of the fp32 atomics
+        tol = 1e-5 if a.dtype == torch.float32 else 1e-2     # (one flipped last bit after rounding to 16 bits)
+        assert rel_err(a.float().cpu().numpy(), b.float().cpu().numpy()) < tol

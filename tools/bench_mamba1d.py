@@ -37,11 +37,11 @@ def timed(fn, n=5, warm=2):
     return e0.elapsed_time(e1) / n
 
 
-def scan_case(B, D, L, N=16, dtype=torch.bfloat16):
+def scan_case(B, D, L, N=16, dtype=torch.bfloat16, G=1):
     g = torch.Generator(device="cuda").manual_seed(0)
     r = lambda *s: torch.randn(*s, device="cuda", generator=g)  # noqa: E731
     u, dl, z = (r(B, D, L).to(dtype).requires_grad_(True) for _ in range(3))
-    Bm, Cm = (r(B, 1, N, L).to(dtype).requires_grad_(True) for _ in range(2))
+    Bm, Cm = (r(B, G, N, L).to(dtype).requires_grad_(True) for _ in range(2))
     A = (-torch.arange(1, N + 1, device="cuda").float().repeat(D, 1)).requires_grad_(True)
     Dp = torch.ones(D, device="cuda", requires_grad=True)
     bias = torch.full((D,), -2.0, device="cuda", requires_grad=True)
@@ -55,7 +55,7 @@ def scan_case(B, D, L, N=16, dtype=torch.bfloat16):
 
     t_fb = timed(fb)
     w = u.element_size()
-    E, S = B * D * L, B * N * L
+    E, S = B * D * L, B * G * N * L
     return t_f, t_fb, w * (5 * E + 2 * S), w * (12 * E + 6 * S)
 
 
@@ -80,6 +80,9 @@ def main():
             y.float().square().mean().backward()
         t = timed(step, n=3, warm=1)
     print(f"cfg 3 Mamba(d_model 32) block fwd+bwd on {tok.shape[1]} tokens (bf16 autocast): {t:.2f} ms = {tok.shape[1] / t / 1e3:.1f} M tokens/s")
+    t_f, t_fb, bf, bfb = scan_case(1, 128, 512 * 512, dtype=torch.float32, G=4)
+    print(f"M2Net batch-1 inference, stage-1 scan (1, 128, 262144) fp32 + z, K = 4: fwd {t_f:.3f} ms {bf / t_f / 1e6:.0f} GB/s "
+          f"({100 * bf / t_f / 1e6 / pk:.1f} %), fwd+bwd {t_fb:.3f} ms")
     for D, L in [(192, 600), (384, 600), (768, 75)]:
         t_f, t_fb, _, _ = scan_case(2, D, L)
         print(f"cfg 4 scan (2, {D}, {L}) bf16 + z: fwd {t_f * 1e3:.0f} us, fwd+bwd {t_fb * 1e3:.0f} us per call (launch-bound)")
