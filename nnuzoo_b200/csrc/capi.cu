@@ -236,15 +236,37 @@ __global__ void __launch_bounds__(128) cp_combine_kernel(const float* __restrict
   float* o = hin + s * nchunks;
   float h = 0.f;
   int c = 0;
-  for (; c + 16 <= nchunks; c += 16) {  // 32 independent loads in flight, then the serial chain
-    float pv[16], gv[16];
+  // There are only rows x 16 such chains, far fewer than the machine has lanes, so the walk is bound by load latency:
+  // 32 links per trip as 16-byte loads, the next trip's 16 loads already in flight while this trip's chain runs.
+  if ((nchunks & 3) == 0) {
+    constexpr int V = 8;  // float4 per array per trip
+    float4 pa[V], ga[V], pb[V], gb[V];
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* o4 = reinterpret_cast<float4*>(o);
+    const int ntrip = nchunks / (4 * V);
+    if (ntrip > 0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) pv[i] = p[c + i], gv[i] = g[c + i];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      o[c + i] = h;
-      h = fmaf(pv[i], h, gv[i]);
+      for (int i = 0; i < V; ++i) pa[i] = p4[i], ga[i] = g4[i];
     }
+    for (int t = 0; t < ntrip; ++t) {
+      if (t + 1 < ntrip) {
+#pragma unroll
+        for (int i = 0; i < V; ++i) pb[i] = p4[(t + 1) * V + i], gb[i] = g4[(t + 1) * V + i];
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float4 r;
+        r.x = h, h = fmaf(pa[i].x, h, ga[i].x);
+        r.y = h, h = fmaf(pa[i].y, h, ga[i].y);
+        r.z = h, h = fmaf(pa[i].z, h, ga[i].z);
+        r.w = h, h = fmaf(pa[i].w, h, ga[i].w);
+        o4[t * V + i] = r;
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) pa[i] = pb[i], ga[i] = gb[i];
+    }
+    c = ntrip * 4 * V;
   }
   for (; c < nchunks; ++c) {
     o[c] = h;
