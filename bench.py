@@ -16,6 +16,12 @@ training step at BASELINE configs[1]: batch 12 x 1x512x512 (scan list: SURVEY.md
              the reference's CPU path (selective_scan_ref restated in oracle/torch_port.py; the
              reference itself is not on the GPU box) on a bounded sample of the same workload.
 
+  train      the second half of BASELINE.json's metric: full SS2D2Net (M2Net) optimisation steps through
+             nnuzoo_b200.train.Trainer (pinned-host batch in, bf16 autocast, Dice+CE deep supervision, backward + DDP
+             all-reduce over NCCL, clip, AdamW, loss read back), 12 patches of 1x512x512 per GPU: patches/s.
+  infer      BASELINE configs[4]: nnuzoo_b200.predict.SlidingWindowPredictor over a synthetic 1x200x512x512 volume,
+             tiles sharded rank::world, gaussian fp16 accumulators merged with one all-reduce each: volumes/s, slices/s.
+
 Multi-GPU (torchrun, one rank per GPU): the scan has no cross-row dependency and the path has no
 exchange step, so every rank runs the full per-GPU batch (weak scaling, "replicas only", no
 collective on the data path); time is the max over ranks.
