@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NZ_ABI_VERSION 2
+#define NZ_ABI_VERSION 3
 
 /* element types of u / delta / B / C / z / out / dout / du / ddelta / dz */
 #define NZ_F32 0
@@ -54,6 +54,9 @@ extern "C" {
 #define NZ_CHUNK 128
 #endif
 #define NZ_MAX_DSTATE 16
+/* Optional second, finer set of checkpoints: h at the end of every NZ_FINE steps (NzScanDesc::xf).  It feeds the
+ * row-per-lane backward (csrc/scan_rl_kernels.cuh), which then needs no intra-warp scan at all. */
+#define NZ_FINE 8
 
 typedef struct NzScanDesc {
   /* ---- problem ---- */
@@ -99,8 +102,8 @@ typedef struct NzScanDesc {
   void* ddelta;             /* (batch, dim, L), contiguous, dtype                         */
   void* dz;                 /* (batch, dim, L), contiguous, dtype; NULL iff z == NULL     */
   float* dA;                /* (dim, N) fp32, contiguous      -- ACCUMULATED INTO: caller zeroes */
-  float* dB;                /* (batch, G, N, L) fp32 contiguous -- ACCUMULATED INTO: caller zeroes */
-  float* dC;                /* (batch, G, N, L) fp32 contiguous -- ACCUMULATED INTO: caller zeroes */
+  float* dB;                /* (batch, G, N, L) fp32 contiguous -- ACCUMULATED INTO: caller zeroes, unless        */
+  float* dC;                /* (batch, G, N, L) fp32 contiguous    nz_scan_bwd_overwrites_dbc() says 1            */
   float* dD;                /* (dim) fp32 or NULL             -- ACCUMULATED INTO: caller zeroes */
   float* ddelta_bias;       /* (dim) fp32 or NULL             -- ACCUMULATED INTO: caller zeroes */
 
@@ -110,6 +113,12 @@ typedef struct NzScanDesc {
                                through which consecutive chunks of a row hand their state over.  Two calls
                                that may run concurrently need separate workspaces. */
   int64_t workspace_bytes;
+
+  /* ---- fine checkpoints (ABI v3; optional) ---- */
+  float* xf;                /* NULL, or nz_scan_fine_bytes() bytes: (batch, dim, L / NZ_FINE, N) fp32, h at the end of
+                               every NZ_FINE-step block.  Written by nz_scan_fwd when non-NULL; nz_scan_bwd given the
+                               same buffer (and a workspace of nz_scan_workspace_bytes_bwd() bytes) runs the row-per-lane
+                               backward, otherwise the warp-scan backward that only needs x. */
 } NzScanDesc;
 
 /* Bytes of scratch a call with this batch / dim needs (same for forward and backward). */
@@ -120,6 +129,19 @@ int64_t nz_scan_workspace_bytes(const NzScanDesc* desc);
  * of handing the state from chunk to chunk, provided `workspace_bytes` >= this value (else it uses the chained scheme).
  * Equals nz_scan_workspace_bytes() for every other shape.  Results are bit-identical either way. */
 int64_t nz_scan_workspace_bytes_cp(const NzScanDesc* desc);
+
+/* Bytes of the fine-checkpoint buffer xf this problem can use, or 0 when the row-per-lane backward does not apply to it
+ * (needs d_state 16, groups of a multiple of 32 rows, TMA-expressible operands: 16-byte aligned bases and strides, rows a
+ * whole number of 128-byte lines).  Only the problem fields, u / delta / B / C / z pointers and strides are read. */
+int64_t nz_scan_fine_bytes(const NzScanDesc* desc);
+
+/* Scratch size for nz_scan_bwd: nz_scan_workspace_bytes() plus, when desc->xf is set and the row-per-lane backward
+ * applies, the per-chunk aggregates of its chunk-parallel decomposition. */
+int64_t nz_scan_workspace_bytes_bwd(const NzScanDesc* desc);
+
+/* 1 when nz_scan_bwd on this problem OVERWRITES dB / dC (every element has a single owner tile, so the caller need not
+ * zero them), 0 when it accumulates with atomics into caller-zeroed buffers. */
+int nz_scan_bwd_overwrites_dbc(const NzScanDesc* desc);
 
 /* Number of NZ_CHUNK-long chunks (second-to-last extent of the checkpoint tensor x). */
 int64_t nz_scan_num_chunks(int64_t seqlen);

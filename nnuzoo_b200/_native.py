@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("NNUZOO_B200_LIB") or os.path.join(_HERE, "lib", "libn
 NZ_F32, NZ_BF16, NZ_F16 = 0, 1, 2
 NZ_CHUNK = int(os.environ.get("NNUZOO_B200_CHUNK", "128"))   # tuning builds may use another interval
 NZ_MAX_DSTATE = 16
-ABI_VERSION = 2
+ABI_VERSION = 3
+NZ_FINE = 8  # steps between two fine checkpoints (NzScanDesc.xf)
 WS_HEADER = 256
 
 _vp = ctypes.c_void_p
@@ -40,6 +41,7 @@ class NzScanDesc(ctypes.Structure):
         ("du", _vp), ("ddelta", _vp), ("dz", _vp), ("dA", _vp), ("dB", _vp), ("dC", _vp), ("dD", _vp),
         ("ddelta_bias", _vp),
         ("workspace", _vp), ("workspace_bytes", _i64),
+        ("xf", _vp),
     ]
 
 
@@ -82,6 +84,12 @@ def lib():
                 L.nz_scan_workspace_bytes.restype = _i64
                 L.nz_scan_workspace_bytes_cp.argtypes = [ctypes.POINTER(NzScanDesc)]
                 L.nz_scan_workspace_bytes_cp.restype = _i64
+                for name in ("nz_scan_fine_bytes", "nz_scan_workspace_bytes_bwd"):
+                    fn = getattr(L, name)
+                    fn.argtypes = [ctypes.POINTER(NzScanDesc)]
+                    fn.restype = _i64
+                L.nz_scan_bwd_overwrites_dbc.argtypes = [ctypes.POINTER(NzScanDesc)]
+                L.nz_scan_bwd_overwrites_dbc.restype = ctypes.c_int
                 for name in ("nz_scan_fwd", "nz_scan_bwd", "nz_scan_fwd_bwd_host"):
                     fn = getattr(L, name)
                     fn.argtypes = [ctypes.POINTER(NzScanDesc), _vp]

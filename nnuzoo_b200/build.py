@@ -1,12 +1,14 @@
 """Build the native library in-tree: nnuzoo_b200/lib/libnnuzoo_b200.so (sm_100a only).
 
 nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with the
-gpurun snapshot.  ``python -m nnuzoo_b200.build [--force]``.
+gpurun snapshot.  ``python -m nnuzoo_b200.build [--force] [-v]``.  Objects are rebuilt only when
+their source, a header they include, the C ABI header or the flags changed.
 """
 from __future__ import annotations
 
 import hashlib
 import os
+import re
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -18,8 +20,9 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libnnuzoo_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-SOURCES = ["capi.cu", "cross_kernels.cu", "conv1d_kernels.cu", "proj_kernels.cu", "norm_kernels.cu", "dwconv_kernels.cu", "epilogue_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", "scan_inst_f16.cu"]
-HEADERS = ["nz_common.cuh", "scan_kernels.cuh", "scan_inst.cuh"]
+SOURCES = ["capi.cu", "cross_kernels.cu", "conv1d_kernels.cu", "proj_kernels.cu", "norm_kernels.cu", "dwconv_kernels.cu",
+           "epilogue_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", "scan_inst_f16.cu", "scan_rl_inst_f32.cu",
+           "scan_rl_inst_bf16.cu", "scan_rl_inst_f16.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-warn-spills"]
 
@@ -31,14 +34,32 @@ def _nvcc() -> str:
     return "nvcc"
 
 
+def _deps(path: str, seen=None) -> list:
+    """The file and every local header it includes (transitively), sorted."""
+    seen = set() if seen is None else seen
+    if path in seen or not os.path.exists(path):
+        return []
+    seen.add(path)
+    with open(path) as fh:
+        text = fh.read()
+    for inc in re.findall(r'#include\s+"([^"]+)"', text):
+        _deps(os.path.normpath(os.path.join(os.path.dirname(path), inc)), seen)
+    return sorted(seen)
+
+
+def _src_stamp(src: str) -> str:
+    h = hashlib.sha256()
+    for f in _deps(os.path.join(CSRC, src)):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stamp() -> str:
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS:
-        with open(os.path.join(CSRC, f), "rb") as fh:
-            h.update(fh.read())
-    with open(os.path.join(INCLUDE, "nnuzoo_b200.h"), "rb") as fh:
-        h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    for s in SOURCES:
+        h.update(_src_stamp(s).encode())
     return h.hexdigest()
 
 
@@ -59,6 +80,9 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        stamp_file, stamp = obj + ".stamp", _src_stamp(src)
+        if not force and os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", os.path.join(CSRC, src), "-o", obj]
         if ccbin:
             cmd += ["-ccbin", ccbin]
@@ -67,6 +91,8 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
+        with open(stamp_file, "w") as f:
+            f.write(stamp)
         return obj
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:

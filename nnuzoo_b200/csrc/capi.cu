@@ -15,6 +15,7 @@
 
 #include "../../include/nnuzoo_b200.h"
 #include "scan_inst.cuh"
+#include "scan_rl_kernels.cuh"
 
 namespace nz {
 
@@ -173,6 +174,8 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   a.out_f32 = (d->out_f32 && d->dtype != NZ_F32) ? 1 : 0;
   const size_t eo = a.out_f32 ? 4 : es;
   a.vec_out = d->out && aligned16(d->out) && (d->out_stride[0] * eo) % 16 == 0 && (d->out_stride[1] * eo) % 16 == 0;
+  a.xf = nullptr;  // set by run_scan when the fine checkpoints apply
+  a.nbt = d->seqlen / NZ_FINE;
   a.vec_grad = (d->seqlen * es) % 16 == 0 && (d->seqlen % 4 == 0) && (!d->du || aligned16(d->du)) &&
                (!d->ddelta || aligned16(d->ddelta)) && (!d->dz || aligned16(d->dz)) && (!d->dB || aligned16(d->dB)) &&
                (!d->dC || aligned16(d->dC));
@@ -295,6 +298,105 @@ static cudaError_t run_fwd_cp(ScanKArgs a, const NzScanDesc* d, bool tma, bool h
   return e;
 }
 
+// ---- row-per-lane backward (csrc/scan_rl_kernels.cuh) -------------------------------------------------------------
+// Applies when a warp can own 32 whole rows of one group and every operand is TMA-expressible.
+static bool rl_shape_ok(const NzScanDesc* d) {
+  if (!d || d->batch < 1 || d->dim < 1 || d->ngroups < 1 || d->seqlen < 1 || d->dim % d->ngroups) return false;
+  if (d->force_generic || d->dstate != NZ_MAX_DSTATE || (d->dim / d->ngroups) % 32 != 0) return false;
+  if (getenv("NZ_NO_RL")) return false;
+  const int64_t rd[2] = {d->dim, d->batch};
+  const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
+  const int64_t ds[2] = {d->delta_stride[1], d->delta_stride[0]};
+  const int64_t zs[2] = {d->z_stride[1], d->z_stride[0]};
+  const int64_t bd[3] = {d->dstate, d->ngroups, d->batch};
+  const int64_t bs[3] = {d->B_stride[2], d->B_stride[1], d->B_stride[0]};
+  const int64_t cs[3] = {d->C_stride[2], d->C_stride[1], d->C_stride[0]};
+  const int64_t L = d->seqlen;
+  if (!tma_ok_rows(d->u, d->dtype, L, rd, us, 2) || !tma_ok_rows(d->delta, d->dtype, L, rd, ds, 2) ||
+      !tma_ok_rows(d->B, d->dtype, L, bd, bs, 3) || !tma_ok_rows(d->C, d->dtype, L, bd, cs, 3))
+    return false;
+  if (d->z && !tma_ok_rows(d->z, d->dtype, L, rd, zs, 2)) return false;
+  return true;
+}
+
+// Chunks along L: enough (row block, chunk) work items to fill the machine about twice over (one warp each, 8 warps
+// per SM), each a whole number of 128-byte tiles.
+static void rl_plan(const NzScanDesc* d, int* nchunks, int* tpc) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long rbt = (long)d->batch * (d->dim / 32);
+  const long ntl = d->seqlen * (long)esize(d->dtype) / 128;
+  long target = 2L * sms * 8;
+  if (const char* e = getenv("NZ_RL_ITEMS")) target = atol(e);  // tuning override
+  long nc = (target + rbt - 1) / rbt;
+  if (nc < 1) nc = 1;
+  if (nc > ntl) nc = ntl;
+  const long t = (ntl + nc - 1) / nc;
+  *tpc = (int)t;
+  *nchunks = (int)((ntl + t - 1) / t);
+}
+
+static int64_t rl_extra_bytes(const NzScanDesc* d) {
+  int nc = 1, tpc = 1;
+  rl_plan(d, &nc, &tpc);
+  if (nc <= 1) return 0;
+  const int64_t one = (((int64_t)d->batch * d->dim * nc * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
+  return 3 * one;
+}
+
+template <typename T>
+static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
+  RlArgs r;
+  memset(&r, 0, sizeof(r));
+  const int64_t rd[2] = {d->dim, d->batch};
+  const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
+  const int64_t ds[2] = {d->delta_stride[1], d->delta_stride[0]};
+  const int64_t zs[2] = {d->z_stride[1], d->z_stride[0]};
+  const int64_t os[2] = {d->dout_stride[1], d->dout_stride[0]};
+  const int64_t bd[3] = {d->dstate, d->ngroups, d->batch};
+  const int64_t bs[3] = {d->B_stride[2], d->B_stride[1], d->B_stride[0]};
+  const int64_t cs[3] = {d->C_stride[2], d->C_stride[1], d->C_stride[0]};
+  const int64_t L = d->seqlen;
+  const int rbox[2] = {32, 1};
+  const int bbox[3] = {NZ_MAX_DSTATE, 1, 1};
+  const int tl = 128 / (int)esize(d->dtype);
+  bool ok = make_map(&r.tm_u, d->dtype, d->u, 2, rd, us, L, rbox, tl) &&
+            make_map(&r.tm_delta, d->dtype, d->delta, 2, rd, ds, L, rbox, tl) &&
+            make_map(&r.tm_dout, d->dtype, d->dout, 2, rd, os, L, rbox, tl) &&
+            make_map(&r.tm_B, d->dtype, d->B, 3, bd, bs, L, bbox, tl) && make_map(&r.tm_C, d->dtype, d->C, 3, bd, cs, L, bbox, tl);
+  if (ok && d->z) ok = make_map(&r.tm_z, d->dtype, d->z, 2, rd, zs, L, rbox, tl);
+  if (!ok) return cudaErrorInvalidValue;
+  r.A = d->A; r.D = d->D; r.bias = d->delta_bias; r.xf = d->xf;
+  r.du = d->du; r.ddelta = d->ddelta; r.dz = d->dz;
+  r.dA = d->dA; r.dB = d->dB; r.dC = d->dC; r.dD = d->dD; r.dbias = d->ddelta_bias;
+  r.L = L; r.A_ds = d->A_stride;
+  r.batch = d->batch; r.dim = d->dim; r.ngroups = d->ngroups; r.dpg = d->dim / d->ngroups;
+  r.nrb = r.dpg / 32;
+  r.ntl = (int)(L * (int64_t)esize(d->dtype) / 128);
+  rl_plan(d, &r.nchunks, &r.tpc);
+  r.softplus = d->delta_softplus;
+  r.single = r.nrb == 1;
+  if (r.nchunks > 1) {
+    const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
+    char* base = reinterpret_cast<char*>(d->workspace) + nz_scan_workspace_bytes(d);
+    r.aggG = reinterpret_cast<float*>(base);
+    r.aggQ = reinterpret_cast<float*>(base + one);
+    r.Rin = reinterpret_cast<float*>(base + 2 * one);
+  }
+  cudaError_t e = launch_scan_bwd_rl<T>(r, d->z != nullptr, st);
+  if (e == cudaSuccess) count_launch(r.nchunks > 1 ? 3 : 1);
+  return e;
+}
+
+static bool rl_bwd_usable(const NzScanDesc* d) {
+  const size_t es = esize(d->dtype);
+  const int64_t rd[2] = {d->dim, d->batch};
+  const int64_t os[2] = {d->dout_stride[1], d->dout_stride[0]};
+  return d->xf && rl_shape_ok(d) && tma_ok_rows(d->dout, d->dtype, d->seqlen, rd, os, 2) && aligned16(d->du) &&
+         aligned16(d->ddelta) && (!d->dz || aligned16(d->dz)) && aligned16(d->dB) && aligned16(d->dC) &&
+         aligned16(d->xf) && (d->seqlen * es) % 128 == 0 && d->workspace_bytes >= nz_scan_workspace_bytes_bwd(d);
+}
+
 static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   int rc = validate(d, bwd);
   if (rc) return rc;
@@ -304,6 +406,19 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   const bool tma = setup_tma(d, a, bwd);
   const bool has_z = d->z != nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (d->xf && !rl_shape_ok(d))
+    return fail(NZ_EINVAL, "xf given but the row-per-lane backward does not apply to this problem (nz_scan_fine_bytes() == 0)");
+  if (!bwd && d->xf) {
+    if (!tma) return fail(NZ_EINVAL, "xf given but the forward cannot take the TMA path for this problem");
+    a.xf = d->xf;
+  }
+  if (bwd && rl_bwd_usable(d)) {
+    cudaError_t e = d->dtype == NZ_F32    ? run_bwd_rl<float>(d, st)
+                    : d->dtype == NZ_BF16 ? run_bwd_rl<__nv_bfloat16>(d, st)
+                                          : run_bwd_rl<__half>(d, st);
+    if (e != cudaSuccess) return fail(NZ_ECUDA, "scan_bwd (row-per-lane) launch failed: %s", cudaGetErrorString(e));
+    return NZ_OK;
+  }
   cudaError_t e = cudaMemsetAsync(d->workspace, 0, (size_t)nz_scan_workspace_bytes(d), st);
   if (e != cudaSuccess) return fail(NZ_ECUDA, "workspace memset failed: %s", cudaGetErrorString(e));
   const bool cp = !bwd && cp_eligible(d) && d->workspace_bytes >= nz_scan_workspace_bytes_cp(d);
@@ -339,6 +454,24 @@ int64_t nz_scan_workspace_bytes_cp(const NzScanDesc* d) {
   const int64_t base = nz_scan_workspace_bytes(d);
   if (base == 0 || d->ngroups < 1 || d->seqlen < 1 || d->dim % d->ngroups) return base;
   return nz::cp_eligible(d) ? base + nz::cp_extra_bytes(d) : base;
+}
+
+int64_t nz_scan_fine_bytes(const NzScanDesc* d) {
+  if (!nz::rl_shape_ok(d) || d->seqlen % NZ_FINE) return 0;
+  return (int64_t)d->batch * d->dim * (d->seqlen / NZ_FINE) * NZ_MAX_DSTATE * (int64_t)sizeof(float);
+}
+
+int64_t nz_scan_workspace_bytes_bwd(const NzScanDesc* d) {
+  const int64_t base = nz_scan_workspace_bytes(d);
+  if (base == 0 || !d->xf || !nz::rl_shape_ok(d)) return base;
+  return base + nz::rl_extra_bytes(d);
+}
+
+int nz_scan_bwd_overwrites_dbc(const NzScanDesc* d) {
+  if (!d || d->ngroups < 1 || d->dim % d->ngroups) return 0;
+  const int dpg = d->dim / d->ngroups;
+  if (d->xf && nz::rl_shape_ok(d)) return dpg == 32 ? 1 : 0;
+  return dpg <= nz::kBwdRows ? 1 : 0;
 }
 
 int nz_scan_fwd(const NzScanDesc* desc, void* stream) { return nz::run_scan(desc, stream, false); }
@@ -432,9 +565,26 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
   }
   {
     const int nsl = (int)(Bt < 64 ? Bt : 64);  // one slice per batch entry (at most 64 slices)
+    // fine checkpoints + the larger backward scratch when the row-per-lane backward applies (device buffers are
+    // 256-byte aligned and dense, so only the shape decides)
+    size_t fine_bytes = 0, ws_bytes = (size_t)nz_scan_workspace_bytes(h);
+    if (bwd) {
+      NzScanDesc q = *h;
+      q.u = q.delta = q.B = q.C = reinterpret_cast<void*>(256);
+      if (h->z) { q.z = reinterpret_cast<void*>(256); q.z_stride[0] = Dm * L; q.z_stride[1] = L; }
+      fine_bytes = (size_t)nz_scan_fine_bytes(&q);
+      if (fine_bytes) {
+        q.xf = reinterpret_cast<float*>(256);
+        for (int64_t nb : {Bt / nsl, (Bt + nsl - 1) / nsl}) {
+          q.batch = (int32_t)nb;
+          const size_t w = (size_t)nz_scan_workspace_bytes_bwd(&q);
+          if (w > ws_bytes) ws_bytes = w;
+        }
+      }
+    }
     const size_t total = 8 * (row_bytes + 256) + 2 * (bc_bytes + 256) + 2 * (bc_f32 + 256) +
                          (size_t)Bt * Dm * nch * N * 4 + 6 * ((size_t)Dm * N * 4 + 256) + 4096 +
-                         (size_t)nz_scan_workspace_bytes(h) + 256;
+                         ws_bytes + 256 + fine_bytes + 256;
     NZ_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&pool), total, st));
     char* du_ = carve(row_bytes); char* dd_ = carve(row_bytes); char* dz_ = carve(row_bytes);
     char* u_ = carve(row_bytes); char* dl_ = carve(row_bytes); char* z_ = carve(row_bytes);
@@ -445,7 +595,8 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
     char* A_ = carve((size_t)Dm * N * 4); char* dA_ = carve((size_t)Dm * N * 4);
     char* D_ = carve((size_t)Dm * 4); char* bias_ = carve((size_t)Dm * 4);
     char* dD_ = carve((size_t)Dm * 4); char* db_ = carve((size_t)Dm * 4);
-    char* ws_ = carve((size_t)nz_scan_workspace_bytes(h));
+    char* ws_ = carve(ws_bytes);
+    char* xf_ = fine_bytes ? carve(fine_bytes) : nullptr;
     // the side streams start after the allocation (and whatever precedes this call on `stream`)
     NZ_CUDA(cudaEventRecord(ev_start, st));
     NZ_CUDA(cudaStreamWaitEvent(s_in, ev_start, 0));
@@ -487,7 +638,8 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
       d.delta_bias = h->delta_bias ? reinterpret_cast<float*>(bias_) : nullptr;
       d.z = h->z ? z_ + ro : nullptr; d.z_stride[0] = Dm * L; d.z_stride[1] = L;
       d.out = out_ + ro; d.x = reinterpret_cast<float*>(x_ + xo);
-      d.workspace = ws_; d.workspace_bytes = nz_scan_workspace_bytes(h);
+      d.workspace = ws_; d.workspace_bytes = (int64_t)ws_bytes;
+      d.xf = xf_ ? reinterpret_cast<float*>(xf_ + (size_t)b0 * Dm * (L / NZ_FINE) * N * 4) : nullptr;
       rc = nz_scan_fwd(&d, stream);
       if (rc) goto done;
       if (bwd) {

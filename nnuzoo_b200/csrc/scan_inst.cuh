@@ -44,11 +44,14 @@ static cudaError_t persistent_grid(K kern, int threads, size_t smem, int ntiles,
   return cudaSuccess;
 }
 
-template <typename T, bool kTMA, bool kHasZ>
+template <typename T, bool kTMA, bool kHasZ, bool kFineCk = false>
 static cudaError_t launch_fwd_one(const ScanKArgs& a, cudaStream_t st) {
+  if constexpr (kTMA && !kFineCk) {
+    if (a.xf && a.cp_mode != 1) return launch_fwd_one<T, kTMA, kHasZ, true>(a, st);
+  }
   using Cfg = ScanCfg<T, NZ_FWD_M, NZ_FWD_LPR, kWarps, kHasZ, false>;
-  auto kern = scan_fwd_kernel<T, NZ_FWD_M, NZ_FWD_LPR, kWarps, NZ_FWD_NQ, kTMA, kHasZ>;
-  const size_t smem = Cfg::smem_bytes(kTMA);
+  auto kern = scan_fwd_kernel<T, NZ_FWD_M, NZ_FWD_LPR, kWarps, NZ_FWD_NQ, kTMA, kHasZ, kFineCk>;
+  const size_t smem = Cfg::smem_bytes(kTMA, kFineCk);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   unsigned grid = 0;

@@ -103,6 +103,8 @@ struct alignas(64) ScanKArgs {
   float *cp_P, *cp_H;
   const float* cp_hin;
   int vec_grad;  // du/ddelta/dz and dB/dC rows 16-byte aligned
+  float* xf;     // fine checkpoints (batch, dim, nbt, 16): h at the end of every NZ_FINE-step block (kFineCk forwards)
+  long nbt;      // fine blocks per row (L / NZ_FINE)
 };
 
 template <typename T, int M, int LPR, int WARPS, bool kHasZ, bool kBwd>
@@ -132,8 +134,10 @@ struct ScanCfg {
   static_assert(ROWTILE % 1024 == 0, "row tiles must keep the 1024-byte swizzle alignment");
   static_assert(SEGB >= 16 && SEGB % 16 == 0, "a lane's segment must be whole 16-byte vectors");
   static_assert(M % 2 == 0, "packed fp32x2 math works on time pairs");
-  static constexpr size_t smem_bytes(bool tma) {
-    return 1024 + (size_t)ROWS_REGION + (size_t)(tma ? 2 : 1) * BC_TX + 5 * (size_t)SLAB + (size_t)GSB + SMALL;
+  static constexpr int FINE_STAGE = WARPS * (M / NZ_FINE) * 4 * 32 * 4;  // per warp [block][state & 3][lane] fp32
+  static constexpr size_t smem_bytes(bool tma, bool fine = false) {
+    return 1024 + (size_t)ROWS_REGION + (size_t)(tma ? 2 : 1) * BC_TX + 5 * (size_t)SLAB + (size_t)GSB + SMALL +
+           (fine ? (size_t)FINE_STAGE : 0);
   }
 };
 
@@ -294,9 +298,10 @@ __device__ __forceinline__ float ks_enter_down_w(float Q, float G, float carry) 
 #ifndef NZ_FWD_MINB
 #define NZ_FWD_MINB 2  // resident CTAs per SM the forward is compiled for (register cap 65536 / (256 * MINB))
 #endif
-template <typename T, int M, int LPR, int WARPS, int NQ, bool kTMA, bool kHasZ>
+template <typename T, int M, int LPR, int WARPS, int NQ, bool kTMA, bool kHasZ, bool kFineCk = false>
 __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LPR > 128) ? 1 : NZ_FWD_MINB)
     scan_fwd_kernel(const __grid_constant__ ScanKArgs a) {
+  static_assert(!kFineCk || (kTMA && M % NZ_FINE == 0), "fine checkpoints: TMA path, whole blocks per lane");
   using Cfg = ScanCfg<T, M, LPR, WARPS, kHasZ, false>;
   constexpr int R = Cfg::R, TL = Cfg::TL, ROWB = Cfg::ROWB, SEGB = Cfg::SEGB, RPW = Cfg::RPW;
   constexpr int ROWTILE = Cfg::ROWTILE, BCTILE = Cfg::BCTILE;
@@ -320,6 +325,9 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
   const uint32_t a2_s0 = rows_s + (uint32_t)(reinterpret_cast<uint8_t*>(sm_A2) - rows);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // staging of the fine checkpoints: [warp][block of the lane's segment][state & 3][lane]
+  [[maybe_unused]] const uint32_t fine_w =
+      a2_s0 + (uint32_t)(Cfg::SMALL - 256) + (uint32_t)(warp * (M / NZ_FINE) * 4 * 32 * 4 + lane * 4);
   const int sl = lane / RPW;                      // segment (time) index inside the row
   const int rloc = warp * RPW + lane % RPW;       // row inside the CTA
   const int N = kTMA ? kMaxState : a.dstate;  // the TMA path only runs d_state == 16
@@ -632,6 +640,26 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
           bv[qi][i] = h[qi];
         }
 #endif
+      }
+      if constexpr (kFineCk) {
+        // h at the end of each 8-step block of the lane's segment -> xf[row][block][state]; four states are gathered
+        // through a lane-private staging column so that the store is one 16-byte vector per block
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+          const int nn = n + qi;
+          const uint32_t fs = fine_w + (uint32_t)((nn & 3) << 7);
+#pragma unroll
+          for (int bk = 0; bk < M / NZ_FINE; ++bk) sts32(fs + bk * 512, bv[qi][bk * NZ_FINE + NZ_FINE - 1]);
+          if ((nn & 3) == 3) {
+#pragma unroll
+            for (int bk = 0; bk < M / NZ_FINE; ++bk) {
+              const long blkg = (long)c * (TL / NZ_FINE) + sl * (M / NZ_FINE) + bk;
+              const float4 v = make_float4(lds32(fine_w + bk * 512), lds32(fine_w + bk * 512 + 128),
+                                           lds32(fine_w + bk * 512 + 256), lds32(fine_w + bk * 512 + 384));
+              if (blkg < a.nbt) *reinterpret_cast<float4*>(a.xf + (rowg * a.nbt + blkg) * kMaxState + (nn - 3)) = v;
+            }
+          }
+        }
       }
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {

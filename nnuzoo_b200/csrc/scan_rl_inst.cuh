@@ -1,0 +1,41 @@
+// scan_rl_inst.cuh -- host-side launch wrapper of the row-per-lane backward; included by one .cu per element type.
+#pragma once
+
+#include "scan_rl_kernels.cuh"
+
+namespace nz {
+
+// Row-per-lane backward: aggregate pass + combine (only when the launch is split into chunks along L) + main pass.
+// One warp per CTA; shared memory, not registers, bounds residency, so the carve-out is set to the maximum once.
+template <typename T, bool kHasZ>
+static cudaError_t launch_rl_one(const RlArgs& a, cudaStream_t st) {
+  auto agg = scan_bwd_rl_agg_kernel<T, kHasZ>;
+  auto maink = scan_bwd_rl_kernel<T, kHasZ>;
+  constexpr size_t agg_smem = 1024 + 2 * ((kHasZ ? 3 : 2) * RlCfg<T>::ROWT + RlCfg<T>::BCT) + 64;
+  constexpr size_t main_smem = RlMainSmem<T, kHasZ>::bytes();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(agg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(maink, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const long rbt = (long)a.batch * a.ngroups * a.nrb;
+  if (a.nchunks > 1) {
+    agg<<<(unsigned)(rbt * (a.nchunks - 1)), 32, agg_smem, st>>>(a);
+    const long nrows = (long)a.batch * a.dim;
+    scan_bwd_rl_combine_kernel<<<(unsigned)((nrows * kMaxState + 127) / 128), 128, 0, st>>>(a.aggG, a.aggQ, a.Rin, nrows,
+                                                                                          a.nchunks);
+  }
+  maink<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+#define NZ_INSTANTIATE_SCAN_RL(T)                                                            \
+  template <>                                                                                \
+  cudaError_t launch_scan_bwd_rl<T>(const RlArgs& a, bool has_z, cudaStream_t stream) {       \
+    return has_z ? launch_rl_one<T, true>(a, stream) : launch_rl_one<T, false>(a, stream);   \
+  }
+
+}  // namespace nz

@@ -21,10 +21,6 @@ from ._native import NzScanDesc
 
 _DTYPES = {torch.float32: _native.NZ_F32, torch.bfloat16: _native.NZ_BF16, torch.float16: _native.NZ_F16}
 
-# rows of one (batch, group) in a backward tile (scan_inst.cuh kBwdRows); when a group has at most
-# this many rows a single tile owns each dB/dC element and no zero-initialisation is needed
-_ROWS_PER_TILE = 16
-
 
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
@@ -53,7 +49,7 @@ def _check_inputs(u, delta, A, B, C, D, z, delta_bias):
         raise NotImplementedError(f"d_state {A.shape[1]} > {_native.NZ_MAX_DSTATE} is not implemented")
 
 
-def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, force_generic, forward=False):
+def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, force_generic, forward=False, xf=None):
     batch, dim, L = u.shape
     desc.batch, desc.dim, desc.dstate, desc.ngroups = batch, dim, A.shape[1], B.shape[1]
     desc.seqlen = L
@@ -76,12 +72,16 @@ def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, forc
     nbytes = _native.workspace_bytes(batch, dim)
     if forward and L >= 4096:
         nbytes = max(nbytes, int(_native.lib().nz_scan_workspace_bytes_cp(ctypes.byref(desc))))
+    if xf is not None:  # backward with fine checkpoints: room for the chunk aggregates of the row-per-lane kernels
+        desc.xf = _ptr(xf)
+        nbytes = max(nbytes, int(_native.lib().nz_scan_workspace_bytes_bwd(ctypes.byref(desc))))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=u.device)
     desc.workspace, desc.workspace_bytes = _ptr(ws), nbytes
     return ws
 
 
 _FORCE_GENERIC = False  # tests flip this to exercise the non-TMA loader on TMA-eligible shapes
+_USE_FINE = True        # tests / tools flip this to run the warp-scan backward on shapes the row-per-lane one takes
 
 
 class SelectiveScanFn(torch.autograd.Function):
@@ -134,6 +134,14 @@ class SelectiveScanFn(torch.autograd.Function):
         x = torch.empty((batch, dim, nchunks, N), dtype=torch.float32, device=u.device)
         desc = NzScanDesc()
         ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC, forward=True)
+        # fine checkpoints (h every NZ_FINE steps) feed the row-per-lane backward; only taken when a gradient will be asked
+        # for and the problem qualifies (nz_scan_fine_bytes() > 0)
+        xf = None
+        if _USE_FINE and any(ctx.needs_input_grad[:8]):
+            nfine = int(lib.nz_scan_fine_bytes(ctypes.byref(desc)))
+            if nfine:
+                xf = torch.empty((nfine // 4,), dtype=torch.float32, device=u.device)
+                desc.xf = _ptr(xf)
         desc.out_f32 = int(out_f32)
         desc.out = _ptr(out)
         desc.out_stride[0], desc.out_stride[1] = out.stride(0), out.stride(1)
@@ -145,7 +153,8 @@ class SelectiveScanFn(torch.autograd.Function):
         ctx.has_z = z is not None
         ctx.has_D = D is not None
         ctx.has_bias = delta_bias is not None
-        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x)
+        ctx.has_xf = xf is not None
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias, x, *([xf] if xf is not None else []))
         if not return_last_state:
             return out
         last_state = x[:, :, -1, :]  # :40 (batch, dim, dstate)
@@ -154,7 +163,8 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout, *args):
-        u, delta, A, B, C, D, z, delta_bias, x = ctx.saved_tensors
+        u, delta, A, B, C, D, z, delta_bias, x = ctx.saved_tensors[:9]
+        xf = ctx.saved_tensors[9] if ctx.has_xf else None
         if dout.stride(-1) != 1 or dout.dtype != u.dtype:  # :57-58
             dout = dout.to(u.dtype).contiguous()
         batch, dim, L = u.shape
@@ -166,15 +176,15 @@ class SelectiveScanFn(torch.autograd.Function):
         ddelta = torch.empty_like(du)
         dz = torch.empty_like(du) if ctx.has_z else None
         dA = torch.zeros((dim, N), dtype=torch.float32, device=dev)
-        dpg = dim // G
-        single_owner = dpg <= _ROWS_PER_TILE
-        mk = torch.empty if single_owner else torch.zeros
-        dB = mk((batch, G, N, L), dtype=torch.float32, device=dev)
-        dC = mk((batch, G, N, L), dtype=torch.float32, device=dev)
         dD = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_D else None
         dbias = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_bias else None
         desc = NzScanDesc()
-        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC)
+        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC, xf=xf)
+        # dB / dC are overwritten when every element has a single owner tile, accumulated into (atomics) otherwise:
+        # the library says which
+        mk = torch.empty if lib.nz_scan_bwd_overwrites_dbc(ctypes.byref(desc)) else torch.zeros
+        dB = mk((batch, G, N, L), dtype=torch.float32, device=dev)
+        dC = mk((batch, G, N, L), dtype=torch.float32, device=dev)
         desc.x = _ptr(x)
         desc.dout = _ptr(dout)
         desc.dout_stride[0], desc.dout_stride[1] = dout.stride(0), dout.stride(1)

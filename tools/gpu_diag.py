@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-STAGES = ["generic_fwd", "generic_bwd", "tma_fwd", "tma_bwd", "tma_z_bf16", "long", "cross"]
+STAGES = ["generic_fwd", "generic_bwd", "tma_fwd", "tma_bwd", "tma_z_bf16", "rl", "rl_z_16bit", "long", "cross"]
 
 
 def run_stage(stage):
@@ -67,6 +67,16 @@ def run_stage(stage):
         print(json.dumps({"tma z fp32": scan_case((2, 16, 1, 16, 512, True), False, True)}))
         print(json.dumps({"tma z bf16": scan_case((2, 16, 1, 16, 512, True), False, True, "bfloat16")}))
         print(json.dumps({"tma z f16": scan_case((2, 16, 1, 16, 512, True), False, True, "float16")}))
+    elif stage == "rl":  # row-per-lane backward: one warp per group / several warps per group (RED) / chunked
+        print(json.dumps({"rl single (2,128,4,16,1024)": scan_case((2, 128, 4, 16, 1024, False), False, True)}))
+        print(json.dumps({"rl red (2,128,2,16,4128)": scan_case((2, 128, 2, 16, 4128, False), False, True)}))
+        os.environ["NZ_RL_ITEMS"] = "1"
+        print(json.dumps({"rl one chunk (2,128,4,16,1024)": scan_case((2, 128, 4, 16, 1024, False), False, True)}))
+        del os.environ["NZ_RL_ITEMS"]
+    elif stage == "rl_z_16bit":
+        print(json.dumps({"rl z fp32": scan_case((2, 64, 1, 16, 2048, True), False, True)}))
+        print(json.dumps({"rl z bf16": scan_case((2, 64, 1, 16, 2048, True), False, True, "bfloat16")}))
+        print(json.dumps({"rl f16": scan_case((2, 64, 2, 16, 2048, False), False, True, "float16")}))
     elif stage == "long":
         print(json.dumps({"cfg1 (2,768,4,16,4096)": scan_case((2, 768, 4, 16, 4096, False), False, True)}))
         print(json.dumps({"stage1 b1 (1,128,4,16,262144)": scan_case((1, 128, 4, 16, 262144, False), False, True)}))

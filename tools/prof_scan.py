@@ -40,8 +40,8 @@ def main():
     bias = torch.full((kd,), -2.0, device=dev)
     dA, dD, db = torch.zeros(kd, N, device=dev), torch.zeros(kd, device=dev), torch.zeros(kd, device=dev)
     nch = (L + _native.NZ_CHUNK - 1) // _native.NZ_CHUNK
-    ws = torch.empty(_native.workspace_bytes(batch, kd), dtype=torch.uint8, device=dev)
     x = torch.empty(batch * kd * nch * N, device=dev)
+    use_fine = os.environ.get("NZ_PROF_FINE", "1") != "0"
     p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     st = torch.cuda.current_stream()
     sp = ctypes.c_void_p(st.cuda_stream)
@@ -58,14 +58,26 @@ def main():
             s[0], s[1], s[2] = G * N * L, N * L, L
         d.A_stride = N
         d.out, d.x, d.du, d.ddelta = p(out), p(x), p(du), p(dd)
-        d.workspace, d.workspace_bytes = p(ws), _native.workspace_bytes(batch, kd)
         d.dA, d.dB, d.dC, d.dD, d.ddelta_bias = p(dA), p(dB), p(dC), p(dD), p(db)
         return d
+
+    # fine checkpoints + the backward's larger scratch when the row-per-lane backward applies
+    d0 = desc(0)
+    nfine = int(lib.nz_scan_fine_bytes(ctypes.byref(d0))) if use_fine else 0
+    xf = torch.empty(max(nfine // 4, 1), device=dev)
+    if nfine:
+        d0.xf = p(xf)
+    wsb = max(int(lib.nz_scan_workspace_bytes_bwd(ctypes.byref(d0))), int(lib.nz_scan_workspace_bytes_cp(ctypes.byref(d0))))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    print(f"fine checkpoints: {nfine} bytes, workspace {wsb} bytes")
 
     E, S = rows, bc
     tf = tb = 0.0
     for it in range(iters + 1):
         d = desc(it % NB)
+        d.workspace, d.workspace_bytes = p(ws), wsb
+        if nfine:
+            d.xf = p(xf)
         e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         dB.zero_()
         dC.zero_()
