@@ -92,6 +92,42 @@ static bool make_map(CUtensorMap* m, int dtype, const void* base, int nouter, co
   return r == CUDA_SUCCESS;
 }
 
+// Tensor map over a (..., rows, L) tensor viewed as (8-step block, blocks per row, outer dims...): a box is then one
+// block of `outer_box` rows -- dense rows of 8 elements (fp32: 32 bytes under SWIZZLE_32B, 16-bit: 16 bytes).  With
+// inner_elems = 16 and fp32 it views the fine checkpoints (..., rows, L / 8, 16) as 64-byte rows under SWIZZLE_64B.
+static bool make_map_blk(CUtensorMap* m, int dtype, const void* base, int inner_elems, int64_t nblocks, int nouter,
+                         const int64_t* outer_dim, const int64_t* outer_stride_elems, const int* outer_box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  const size_t es = esize(dtype);
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  dims[0] = (cuuint64_t)inner_elems;
+  dims[1] = (cuuint64_t)nblocks;
+  strides[0] = (cuuint64_t)inner_elems * es;
+  box[0] = (cuuint32_t)inner_elems;
+  box[1] = 1;
+  const cuuint64_t safe = (cuuint64_t)nblocks * inner_elems * es;
+  for (int i = 0; i < nouter; ++i) {
+    dims[2 + i] = (cuuint64_t)outer_dim[i];
+    cuuint64_t sb = (cuuint64_t)outer_stride_elems[i] * es;
+    if (outer_dim[i] == 1 && (sb == 0 || sb % 16 != 0)) sb = safe;
+    strides[1 + i] = sb;
+    box[2 + i] = (cuuint32_t)outer_box[i];
+  }
+  const CUtensorMapDataType dt = dtype == NZ_F32    ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == NZ_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                                    : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const size_t row_bytes = (size_t)inner_elems * es;
+  const CUtensorMapSwizzle sw = row_bytes == 64   ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(m, dt, (cuuint32_t)(2 + nouter), const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // TMA can express a (batch, rows, L) operand iff every stride is a 16-byte multiple, the base is
@@ -319,14 +355,15 @@ static bool rl_shape_ok(const NzScanDesc* d) {
   return true;
 }
 
-// Chunks along L: enough (row block, chunk) work items to fill the machine about twice over (one warp each, 8 warps
-// per SM), each a whole number of 128-byte tiles.
+// Chunks along L: (row block, chunk) work items are one warp each and 8 warps are resident per SM; all items cost the
+// same, so the launch is cut into about 8 waves of them (two full waves plus 32 stragglers measured 2.14 ms where 1.43
+// would do: profiles/r02_kernel_tuning.md), each chunk a whole number of 128-byte tiles.
 static void rl_plan(const NzScanDesc* d, int* nchunks, int* tpc) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long rbt = (long)d->batch * (d->dim / 32);
   const long ntl = d->seqlen * (long)esize(d->dtype) / 128;
-  long target = 2L * sms * 8;
+  long target = 8L * sms * 8;
   if (const char* e = getenv("NZ_RL_ITEMS")) target = atol(e);  // tuning override
   long nc = (target + rbt - 1) / rbt;
   if (nc < 1) nc = 1;
@@ -360,11 +397,20 @@ static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
   const int rbox[2] = {32, 1};
   const int bbox[3] = {NZ_MAX_DSTATE, 1, 1};
   const int tl = 128 / (int)esize(d->dtype);
-  bool ok = make_map(&r.tm_u, d->dtype, d->u, 2, rd, us, L, rbox, tl) &&
-            make_map(&r.tm_delta, d->dtype, d->delta, 2, rd, ds, L, rbox, tl) &&
-            make_map(&r.tm_dout, d->dtype, d->dout, 2, rd, os, L, rbox, tl) &&
-            make_map(&r.tm_B, d->dtype, d->B, 3, bd, bs, L, bbox, tl) && make_map(&r.tm_C, d->dtype, d->C, 3, bd, cs, L, bbox, tl);
-  if (ok && d->z) ok = make_map(&r.tm_z, d->dtype, d->z, 2, rd, zs, L, rbox, tl);
+  const int64_t nbt = L / NZ_FINE;
+  const int64_t xs[2] = {nbt * NZ_MAX_DSTATE, (int64_t)d->dim * nbt * NZ_MAX_DSTATE};
+  // main pass: per-block boxes
+  bool ok = make_map_blk(&r.tm_u, d->dtype, d->u, NZ_FINE, nbt, 2, rd, us, rbox) &&
+            make_map_blk(&r.tm_delta, d->dtype, d->delta, NZ_FINE, nbt, 2, rd, ds, rbox) &&
+            make_map_blk(&r.tm_dout, d->dtype, d->dout, NZ_FINE, nbt, 2, rd, os, rbox) &&
+            make_map_blk(&r.tm_B, d->dtype, d->B, NZ_FINE, nbt, 3, bd, bs, bbox) &&
+            make_map_blk(&r.tm_C, d->dtype, d->C, NZ_FINE, nbt, 3, bd, cs, bbox) &&
+            make_map_blk(&r.tm_xf, NZ_F32, d->xf, NZ_MAX_DSTATE, nbt, 2, rd, xs, rbox);
+  if (ok && d->z) ok = make_map_blk(&r.tm_z, d->dtype, d->z, NZ_FINE, nbt, 2, rd, zs, rbox);
+  // aggregate pass: per-tile boxes (128 bytes of a row)
+  ok = ok && make_map(&r.g_delta, d->dtype, d->delta, 2, rd, ds, L, rbox, tl) &&
+       make_map(&r.g_row1, d->dtype, d->dout, 2, rd, os, L, rbox, tl) && make_map(&r.g_bc, d->dtype, d->C, 3, bd, cs, L, bbox, tl);
+  if (ok && d->z) ok = make_map(&r.g_z, d->dtype, d->z, 2, rd, zs, L, rbox, tl);
   if (!ok) return cudaErrorInvalidValue;
   r.A = d->A; r.D = d->D; r.bias = d->delta_bias; r.xf = d->xf;
   r.du = d->du; r.ddelta = d->ddelta; r.dz = d->dz;
@@ -388,6 +434,62 @@ static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
   return e;
 }
 
+// Row-per-lane forward: same eligibility; also writes the fine checkpoints when d->xf is set.
+template <typename T>
+static cudaError_t run_fwd_rl(const NzScanDesc* d, cudaStream_t st) {
+  RlArgs r;
+  memset(&r, 0, sizeof(r));
+  const int64_t rd[2] = {d->dim, d->batch};
+  const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
+  const int64_t ds[2] = {d->delta_stride[1], d->delta_stride[0]};
+  const int64_t zs[2] = {d->z_stride[1], d->z_stride[0]};
+  const int64_t bd[3] = {d->dstate, d->ngroups, d->batch};
+  const int64_t bs[3] = {d->B_stride[2], d->B_stride[1], d->B_stride[0]};
+  const int64_t cs[3] = {d->C_stride[2], d->C_stride[1], d->C_stride[0]};
+  const int64_t L = d->seqlen;
+  const int rbox[2] = {32, 1};
+  const int bbox[3] = {NZ_MAX_DSTATE, 1, 1};
+  const int tl = 128 / (int)esize(d->dtype);
+  const int64_t nbt = L / NZ_FINE;
+  bool ok = make_map_blk(&r.tm_u, d->dtype, d->u, NZ_FINE, nbt, 2, rd, us, rbox) &&
+            make_map_blk(&r.tm_delta, d->dtype, d->delta, NZ_FINE, nbt, 2, rd, ds, rbox) &&
+            make_map_blk(&r.tm_B, d->dtype, d->B, NZ_FINE, nbt, 3, bd, bs, bbox) &&
+            make_map_blk(&r.tm_C, d->dtype, d->C, NZ_FINE, nbt, 3, bd, cs, bbox);
+  if (ok && d->z) ok = make_map_blk(&r.tm_z, d->dtype, d->z, NZ_FINE, nbt, 2, rd, zs, rbox);
+  ok = ok && make_map(&r.g_delta, d->dtype, d->delta, 2, rd, ds, L, rbox, tl) &&
+       make_map(&r.g_row1, d->dtype, d->u, 2, rd, us, L, rbox, tl) && make_map(&r.g_bc, d->dtype, d->B, 3, bd, bs, L, bbox, tl);
+  if (!ok) return cudaErrorInvalidValue;
+  r.A = d->A; r.D = d->D; r.bias = d->delta_bias;
+  r.out = d->out; r.x = d->x; r.xfw = d->xf;
+  r.o_bs = d->out_stride[0]; r.o_ds = d->out_stride[1];
+  r.nck = (int)nz_scan_num_chunks(L);
+  r.out_f32 = (d->out_f32 && d->dtype != NZ_F32) ? 1 : 0;
+  r.L = L; r.A_ds = d->A_stride;
+  r.batch = d->batch; r.dim = d->dim; r.ngroups = d->ngroups; r.dpg = d->dim / d->ngroups;
+  r.nrb = r.dpg / 32;
+  r.ntl = (int)(L * (int64_t)esize(d->dtype) / 128);
+  rl_plan(d, &r.nchunks, &r.tpc);
+  r.softplus = d->delta_softplus;
+  if (r.nchunks > 1) {
+    const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
+    char* base = reinterpret_cast<char*>(d->workspace) + nz_scan_workspace_bytes(d);
+    r.aggG = reinterpret_cast<float*>(base);
+    r.aggQ = reinterpret_cast<float*>(base + one);
+    r.Rin = reinterpret_cast<float*>(base + 2 * one);
+  }
+  cudaError_t e = launch_scan_fwd_rl<T>(r, d->z != nullptr, st);
+  if (e == cudaSuccess) count_launch(r.nchunks > 1 ? 3 : 1);
+  return e;
+}
+
+static bool rl_fwd_usable(const NzScanDesc* d) {
+  if (getenv("NZ_NO_RL_FWD") || !rl_shape_ok(d)) return false;
+  const size_t eo = (d->out_f32 && d->dtype != NZ_F32) ? 4 : esize(d->dtype);
+  return aligned16(d->out) && (d->out_stride[0] * eo) % 16 == 0 && (d->out_stride[1] * eo) % 16 == 0 &&
+         (!d->xf || aligned16(d->xf)) && aligned16(d->x) &&
+         d->workspace_bytes >= nz_scan_workspace_bytes(d) + rl_extra_bytes(d);
+}
+
 static bool rl_bwd_usable(const NzScanDesc* d) {
   const size_t es = esize(d->dtype);
   const int64_t rd[2] = {d->dim, d->batch};
@@ -408,6 +510,13 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (d->xf && !rl_shape_ok(d))
     return fail(NZ_EINVAL, "xf given but the row-per-lane backward does not apply to this problem (nz_scan_fine_bytes() == 0)");
+  if (!bwd && rl_fwd_usable(d)) {
+    cudaError_t e = d->dtype == NZ_F32    ? run_fwd_rl<float>(d, st)
+                    : d->dtype == NZ_BF16 ? run_fwd_rl<__nv_bfloat16>(d, st)
+                                          : run_fwd_rl<__half>(d, st);
+    if (e != cudaSuccess) return fail(NZ_ECUDA, "scan_fwd (row-per-lane) launch failed: %s", cudaGetErrorString(e));
+    return NZ_OK;
+  }
   if (!bwd && d->xf) {
     if (!tma) return fail(NZ_EINVAL, "xf given but the forward cannot take the TMA path for this problem");
     a.xf = d->xf;
@@ -453,7 +562,12 @@ int64_t nz_scan_workspace_bytes(const NzScanDesc* d) {
 int64_t nz_scan_workspace_bytes_cp(const NzScanDesc* d) {
   const int64_t base = nz_scan_workspace_bytes(d);
   if (base == 0 || d->ngroups < 1 || d->seqlen < 1 || d->dim % d->ngroups) return base;
-  return nz::cp_eligible(d) ? base + nz::cp_extra_bytes(d) : base;
+  int64_t best = nz::cp_eligible(d) ? base + nz::cp_extra_bytes(d) : base;
+  if (nz::rl_shape_ok(d)) {  // the row-per-lane forward keeps its chunk aggregates there
+    const int64_t rl = base + nz::rl_extra_bytes(d);
+    if (rl > best) best = rl;
+  }
+  return best;
 }
 
 int64_t nz_scan_fine_bytes(const NzScanDesc* d) {
@@ -568,18 +682,18 @@ int nz_scan_fwd_bwd_host(const NzScanDesc* h, void* stream) {
     // fine checkpoints + the larger backward scratch when the row-per-lane backward applies (device buffers are
     // 256-byte aligned and dense, so only the shape decides)
     size_t fine_bytes = 0, ws_bytes = (size_t)nz_scan_workspace_bytes(h);
-    if (bwd) {
+    {
       NzScanDesc q = *h;
       q.u = q.delta = q.B = q.C = reinterpret_cast<void*>(256);
       if (h->z) { q.z = reinterpret_cast<void*>(256); q.z_stride[0] = Dm * L; q.z_stride[1] = L; }
-      fine_bytes = (size_t)nz_scan_fine_bytes(&q);
-      if (fine_bytes) {
-        q.xf = reinterpret_cast<float*>(256);
-        for (int64_t nb : {Bt / nsl, (Bt + nsl - 1) / nsl}) {
-          q.batch = (int32_t)nb;
-          const size_t w = (size_t)nz_scan_workspace_bytes_bwd(&q);
-          if (w > ws_bytes) ws_bytes = w;
-        }
+      if (bwd) fine_bytes = (size_t)nz_scan_fine_bytes(&q);
+      if (fine_bytes) q.xf = reinterpret_cast<float*>(256);
+      for (int64_t nb : {Bt / nsl, (Bt + nsl - 1) / nsl}) {
+        q.batch = (int32_t)nb;
+        size_t w = (size_t)nz_scan_workspace_bytes_cp(&q);
+        if (w > ws_bytes) ws_bytes = w;
+        w = (size_t)nz_scan_workspace_bytes_bwd(&q);
+        if (w > ws_bytes) ws_bytes = w;
       }
     }
     const size_t total = 8 * (row_bytes + 256) + 2 * (bc_bytes + 256) + 2 * (bc_f32 + 256) +

@@ -9,10 +9,42 @@ namespace nz {
 // One warp per CTA; shared memory, not registers, bounds residency, so the carve-out is set to the maximum once.
 template <typename T, bool kHasZ>
 static cudaError_t launch_rl_one(const RlArgs& a, cudaStream_t st) {
-  auto agg = scan_bwd_rl_agg_kernel<T, kHasZ>;
-  auto maink = scan_bwd_rl_kernel<T, kHasZ>;
+  auto agg = scan_rl_agg_kernel<T, kHasZ, false>;
+  auto maink1 = scan_bwd_rl_kernel<T, kHasZ, true>;   // one warp per group: plain dB / dC stores
+  auto maink0 = scan_bwd_rl_kernel<T, kHasZ, false>;  // several warps per group: RED
   constexpr size_t agg_smem = 1024 + 2 * ((kHasZ ? 3 : 2) * RlCfg<T>::ROWT + RlCfg<T>::BCT) + 64;
   constexpr size_t main_smem = RlMainSmem<T, kHasZ>::bytes();
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(agg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(maink0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(maink1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const long rbt = (long)a.batch * a.ngroups * a.nrb;
+  if (a.nchunks > 1) {
+    agg<<<(unsigned)(rbt * (a.nchunks - 1)), 32, agg_smem, st>>>(a);
+    const long nrows = (long)a.batch * a.dim;
+    scan_rl_combine_kernel<<<(unsigned)((nrows * kMaxState + 127) / 128), 128, 0, st>>>(a.aggG, a.aggQ, a.Rin, nrows,
+                                                                                      a.nchunks, 0);
+  }
+  if (a.single)
+    maink1<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
+  else
+    maink0<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+// Row-per-lane forward: aggregate pass + combine (chunked launches only) + main pass.
+template <typename T, bool kHasZ>
+static cudaError_t launch_rl_fwd_one(const RlArgs& a, cudaStream_t st) {
+  auto agg = scan_rl_agg_kernel<T, false, true>;
+  auto maink = scan_fwd_rl_kernel<T, kHasZ>;
+  constexpr size_t agg_smem = 1024 + 2 * (2 * RlCfg<T>::ROWT + RlCfg<T>::BCT) + 64;
+  constexpr size_t main_smem = RlFwdSmem<T, kHasZ>::bytes();
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(agg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -25,8 +57,8 @@ static cudaError_t launch_rl_one(const RlArgs& a, cudaStream_t st) {
   if (a.nchunks > 1) {
     agg<<<(unsigned)(rbt * (a.nchunks - 1)), 32, agg_smem, st>>>(a);
     const long nrows = (long)a.batch * a.dim;
-    scan_bwd_rl_combine_kernel<<<(unsigned)((nrows * kMaxState + 127) / 128), 128, 0, st>>>(a.aggG, a.aggQ, a.Rin, nrows,
-                                                                                          a.nchunks);
+    scan_rl_combine_kernel<<<(unsigned)((nrows * kMaxState + 127) / 128), 128, 0, st>>>(a.aggG, a.aggQ, a.Rin, nrows,
+                                                                                      a.nchunks, 1);
   }
   maink<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
   return cudaGetLastError();
@@ -36,6 +68,10 @@ static cudaError_t launch_rl_one(const RlArgs& a, cudaStream_t st) {
   template <>                                                                                \
   cudaError_t launch_scan_bwd_rl<T>(const RlArgs& a, bool has_z, cudaStream_t stream) {       \
     return has_z ? launch_rl_one<T, true>(a, stream) : launch_rl_one<T, false>(a, stream);   \
+  }                                                                                          \
+  template <>                                                                                \
+  cudaError_t launch_scan_fwd_rl<T>(const RlArgs& a, bool has_z, cudaStream_t stream) {       \
+    return has_z ? launch_rl_fwd_one<T, true>(a, stream) : launch_rl_fwd_one<T, false>(a, stream); \
   }
 
 }  // namespace nz

@@ -35,13 +35,21 @@ constexpr int kFine = NZ_FINE;  // steps per block = fine checkpoint interval
 static_assert(kFine == 8, "the row-lane kernels are written for 8-step blocks");
 
 struct alignas(64) RlArgs {
-  CUtensorMap tm_u, tm_delta, tm_dout, tm_z, tm_B, tm_C;
+  // main pass: per-block boxes (8 steps).  aggregate pass: per-tile boxes (128 bytes of a row): the g_ maps
+  CUtensorMap tm_u, tm_delta, tm_dout, tm_z, tm_B, tm_C, tm_xf;
+  CUtensorMap g_delta, g_row1, g_z, g_bc;  // row1 / bc: dout and C (backward), u and B (forward)
   const float *A, *D, *bias;
   const float* xf;     // (batch, dim, L/8, 16): h at the end of every 8-step block
   void *du, *ddelta, *dz;
   float *dA, *dB, *dC, *dD, *dbias;
-  float *aggG, *aggQ;  // [row][chunk][16] aggregates of the reverse recurrence (aggregate pass out)
-  float* Rin;          // [row][chunk][16] R entering every chunk (combine out, main pass in)
+  float *aggG, *aggQ;  // [row][chunk][16] aggregates (G: value leaving the chunk from a zero start, Q: product of a)
+  float* Rin;          // [row][chunk][16] state entering every chunk (combine out, main pass in): R for the backward,
+                       // h for the forward
+  void* out;           // forward: (batch, dim, L) result (T, or fp32 when out_f32)
+  float* x;            // forward: coarse checkpoints (batch, dim, nck, 16)
+  float* xfw;          // forward: fine checkpoints to write (may be NULL)
+  long o_bs, o_ds;     // out strides (elements)
+  int nck, out_f32;
   long L;
   long A_ds;
   int batch, dim, ngroups, dpg;
@@ -51,6 +59,7 @@ struct alignas(64) RlArgs {
   int nchunks;   // chunks along L
   int softplus;
   int single;    // one warp owns each dB / dC element (dpg == 32): plain stores instead of RED
+  unsigned zero; // always 0 (see order_after)
 };
 
 template <typename T>
@@ -64,6 +73,14 @@ struct RlCfg {
 };
 
 // ---- small helpers ----
+// Scheduling fence: `x` may not be consumed before `dep` has been produced.  ptxas otherwise clumps a latency chain
+// (LDS -> FADD2 -> SHFL -> FADD ...) right behind its first load and the in-order warp sits on the scoreboard with
+// independent work queued behind it (profiles/r02_kernel_tuning.md: 45 % of the state loop's samples).  An empty asm
+// only orders the PTX, which ptxas reschedules freely; this is one real LOP3, x |= dep & zero, with a zero ptxas cannot
+// see through (RlArgs::zero, a kernel argument).
+__device__ __forceinline__ void order_after(float& x, float dep, unsigned zero) {
+  asm volatile("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+f"(x) : "f"(dep), "r"(zero));
+}
 __device__ __forceinline__ void stg64_or_red(float* p, float x, float y, bool single) {
   if (single) {
     *reinterpret_cast<float2*>(p) = make_float2(x, y);
@@ -91,11 +108,26 @@ __device__ __forceinline__ void lds_block(uint32_t tile_s, int row, int blk, flo
   }
 }
 
+// state n's 8 steps out of a per-block B / C tile [16 states][8 steps] (every lane reads the same address: broadcast)
+template <typename T>
+__device__ __forceinline__ void lds_bc(uint32_t tile_s, int n, float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    const uint32_t base = tile_s + (uint32_t)n * 32u;
+    const uint32_t sw = (uint32_t)((n >> 2) & 1) << 4;
+    unpack16<T>(lds128(base + sw), &v[0]);
+    unpack16<T>(lds128(base + (sw ^ 16u)), &v[4]);
+  } else {
+    unpack16<T>(lds128(tile_s + (uint32_t)n * 16u), &v[0]);
+  }
+}
+
 // ================================================================================================
 // Aggregate pass: (Q, G) of the reverse recurrence per (row, chunk, state)
 // ================================================================================================
-template <typename T, bool kHasZ>
-__global__ void __launch_bounds__(32, 10) scan_bwd_rl_agg_kernel(const __grid_constant__ RlArgs a) {
+// kFwd = false: reverse recurrence R_{t-1} = a_t (C_t dy_t + R_t) over (delta, dout, [z], C);  chunks 1 .. nchunks-1
+// kFwd = true : forward recurrence h_t = a_t h_{t-1} + dl_t u_t B_t over (delta, u, B);        chunks 0 .. nchunks-2
+template <typename T, bool kHasZ, bool kFwd>
+__global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_constant__ RlArgs a) {
   using Cfg = RlCfg<T>;
   constexpr int TB = Cfg::TB, NBLK = Cfg::NBLK, ROWT = Cfg::ROWT, BCT = Cfg::BCT;
   constexpr int NROW = kHasZ ? 3 : 2;               // delta, dout, [z]
@@ -106,10 +138,10 @@ __global__ void __launch_bounds__(32, 10) scan_bwd_rl_agg_kernel(const __grid_co
   const uint32_t smem_s = smem_u32(smem);
   const int lane = threadIdx.x;
 
-  // work item: chunks 1 .. nchunks-1 (nobody needs the aggregate of the first chunk in time)
+  // work item: nobody needs the aggregate of the first (backward) / last (forward) chunk in time
   const int nc1 = a.nchunks - 1;
   const int item = blockIdx.x;
-  const int c = item % nc1 + 1;
+  const int c = item % nc1 + (kFwd ? 0 : 1);
   int w = item / nc1;
   const int rb = w % a.nrb;
   w /= a.nrb;
@@ -121,17 +153,19 @@ __global__ void __launch_bounds__(32, 10) scan_bwd_rl_agg_kernel(const __grid_co
   auto issue = [&](int t, int s) {
     uint8_t* st = smem + s * STAGE;
     mbar_arrive_expect_tx(&bars[s], STAGE);
-    tma_load_4d(st, &a.tm_delta, &bars[s], 0, t, d0, b);
-    tma_load_4d(st + ROWT, &a.tm_dout, &bars[s], 0, t, d0, b);
-    if (kHasZ) tma_load_4d(st + 2 * ROWT, &a.tm_z, &bars[s], 0, t, d0, b);
-    tma_load_5d(st + NROW * ROWT, &a.tm_C, &bars[s], 0, t, 0, g, b);
+    tma_load_4d(st, &a.g_delta, &bars[s], 0, t, d0, b);
+    tma_load_4d(st + ROWT, &a.g_row1, &bars[s], 0, t, d0, b);
+    if (kHasZ) tma_load_4d(st + 2 * ROWT, &a.g_z, &bars[s], 0, t, d0, b);
+    tma_load_5d(st + NROW * ROWT, &a.g_bc, &bars[s], 0, t, 0, g, b);
   };
+  const int nt = t_hi - t_lo;
+  auto tile_of = [&](int k) { return kFwd ? t_lo + k : t_hi - 1 - k; };  // k-th tile in walking order
   if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     fence_mbar_init();
-    issue(t_hi - 1, 0);
-    if (t_hi - 2 >= t_lo) issue(t_hi - 2, 1);
+    issue(tile_of(0), 0);
+    if (nt > 1) issue(tile_of(1), 1);
   }
   __syncwarp();
 
@@ -144,14 +178,14 @@ __global__ void __launch_bounds__(32, 10) scan_bwd_rl_agg_kernel(const __grid_co
   const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
   float dlsum = 0.f;
 
-  int k = 0;
-  for (int t = t_hi - 1; t >= t_lo; --t, ++k) {
+  for (int k = 0; k < nt; ++k) {
     const int s = k & 1;
     mbar_wait(&bars[s], (k >> 1) & 1);
     const uint32_t st = smem_s + s * STAGE;
 #pragma unroll 1
-    for (int blk = NBLK - 1; blk >= 0; --blk) {
-      float dl[8], dy[8];
+    for (int bi = 0; bi < NBLK; ++bi) {
+      const int blk = kFwd ? bi : NBLK - 1 - bi;
+      float dl[8], dy[8];  // dy: dout (backward) / u (forward)
       lds_block<T>(st, lane, blk, dl);
       lds_block<T>(st + ROWT, lane, blk, dy);
       if constexpr (kHasZ) {
@@ -166,22 +200,25 @@ __global__ void __launch_bounds__(32, 10) scan_bwd_rl_agg_kernel(const __grid_co
         if (a.softplus) x = softplus_f(x);
         dl[i] = x;
         dlsum += x;
+        if (kFwd) dy[i] *= x;  // dl_t u_t
       }
 #pragma unroll
       for (int n = 0; n < kMaxState; ++n) {
         float cv[8];
         lds_block<T>(st + NROW * ROWT, n, blk, cv);
         float r = R[n];
+        if constexpr (kFwd) {
 #pragma unroll
-        for (int i = 7; i >= 0; --i) {
-          const float av = ex2_approx(A2[n] * dl[i]);
-          r = av * fmaf(cv[i], dy[i], r);  // R_{t-1} = a_t (C_t dy_t + R_t)
+          for (int i = 0; i < 8; ++i) r = fmaf(ex2_approx(A2[n] * dl[i]), r, cv[i] * dy[i]);  // h_t = a_t h_{t-1} + b_t
+        } else {
+#pragma unroll
+          for (int i = 7; i >= 0; --i) r = ex2_approx(A2[n] * dl[i]) * fmaf(cv[i], dy[i], r);  // R_{t-1} = a_t (C_t dy_t + R_t)
         }
         R[n] = r;
       }
     }
     __syncwarp();  // every lane is done with stage s
-    if (lane == 0 && t - 2 >= t_lo) issue(t - 2, s);
+    if (lane == 0 && k + 2 < nt) issue(tile_of(k + 2), s);
   }
   float* G = a.aggG + (rowg * a.nchunks + c) * kMaxState;
   float* Q = a.aggQ + (rowg * a.nchunks + c) * kMaxState;
@@ -193,53 +230,83 @@ __global__ void __launch_bounds__(32, 10) scan_bwd_rl_agg_kernel(const __grid_co
   }
 }
 
-// R entering every chunk: one thread per (row, state) walks the chunks last to first
-static __global__ void __launch_bounds__(128) scan_bwd_rl_combine_kernel(const float* __restrict__ G, const float* __restrict__ Q,
-                                                                 float* __restrict__ Rin, long nrows, int nchunks) {
+// State entering every chunk: one thread per (row, state) walks the chunks, last to first for the backward (R), first
+// to last for the forward (h)
+static __global__ void __launch_bounds__(128) scan_rl_combine_kernel(const float* __restrict__ G, const float* __restrict__ Q,
+                                                                    float* __restrict__ Rin, long nrows, int nchunks,
+                                                                    int fwd) {
   const long i = blockIdx.x * 128L + threadIdx.x;
   if (i >= nrows * kMaxState) return;
   const long row = i / kMaxState;
   const int n = (int)(i % kMaxState);
   const long base = row * nchunks * kMaxState + n;
   float r = 0.f;
-  Rin[base + (long)(nchunks - 1) * kMaxState] = 0.f;
-  for (int c = nchunks - 2; c >= 0; --c) {
-    r = fmaf(Q[base + (long)(c + 1) * kMaxState], r, G[base + (long)(c + 1) * kMaxState]);
-    Rin[base + (long)c * kMaxState] = r;
+  if (fwd) {
+    Rin[base] = 0.f;
+    for (int c = 1; c < nchunks; ++c) {
+      r = fmaf(Q[base + (long)(c - 1) * kMaxState], r, G[base + (long)(c - 1) * kMaxState]);
+      Rin[base + (long)c * kMaxState] = r;
+    }
+  } else {
+    Rin[base + (long)(nchunks - 1) * kMaxState] = 0.f;
+    for (int c = nchunks - 2; c >= 0; --c) {
+      r = fmaf(Q[base + (long)(c + 1) * kMaxState], r, G[base + (long)(c + 1) * kMaxState]);
+      Rin[base + (long)c * kMaxState] = r;
+    }
   }
 }
 
 // ================================================================================================
 // Main pass
 // ================================================================================================
-// Shared memory of one warp (bytes):
-//   rows   NROWT x 4096   u, delta, dout, [z] tiles (single-buffered; the next tile is requested as soon as the last
-//                         block of this one sits in registers)
-//   bc     2 x 2 x 2048   B, C tiles, double-buffered
-//   slab   2 x 1152       dB / dC products of one (state, block): 4 groups of 8 rows, 288-byte group pitch
-// A warp is one CTA and shared memory caps residency at 8-9 warps per SM, so registers are free (up to 255): the state
-// loop is fully unrolled and A, R (the carried reverse state) and the dA partial sums of all 16 states live in registers.
+// Operands arrive per BLOCK (8 steps) through a 2-stage TMA ring: a block lasts ~5 us per warp, far longer than the
+// DRAM latency, so one block of look-ahead is all the buffering needed and shared memory stays small enough for 12
+// resident warps per SM (the first version buffered 32-step tiles: 27 KB per warp, 8 warps, issue slots 41 % busy).
+//   rows   2 stages x {u, delta, dout, [z]} x 32 rows x (8 steps)       fp32: 32-byte rows, SWIZZLE_32B
+//   xf     2 stages x 32 rows x 64 bytes (h entering the block)         SWIZZLE_64B
+//   bc     2 stages x {B, C} x 16 states x (8 steps)
+//   slab   2 x 2 x 1152   dB / dC products of one (state, block): 4 groups of 8 rows, 288-byte group pitch; double-
+//                         buffered so that state n-1 is reduced while the recurrences of state n run
 template <typename T, bool kHasZ>
 struct RlMainSmem {
   static constexpr int NROWT = kHasZ ? 4 : 3;
-  static constexpr int ROWS = NROWT * RlCfg<T>::ROWT;
-  static constexpr int BC = 2 * 2 * RlCfg<T>::BCT;
+  static constexpr int RB = 32 * kFine * (int)sizeof(T);        // one row array of one block (1024 / 512 bytes)
+  static constexpr int XB = 32 * kMaxState * 4;                 // fine checkpoints of one block (2048 bytes)
+  static constexpr int RSTAGE = ((NROWT * RB + 1023) / 1024) * 1024 + XB;  // xf sits 1024-aligned after the row arrays
+  static constexpr int OFF_XF = RSTAGE - XB;
+  static constexpr int BB = kMaxState * kFine * (int)sizeof(T); // one B or C array of one block (512 / 256 bytes)
+  static constexpr int BSTAGE = 2 * BB;
   static constexpr int SLAB1 = 4 * 288;
   static constexpr int SLAB = 2 * SLAB1;
-  static constexpr int OFF_BC = ROWS, OFF_SLAB = OFF_BC + BC, OFF_BARS = OFF_SLAB + ((SLAB + 127) / 128) * 128;
+  static constexpr int OFF_BC = 2 * RSTAGE, OFF_SLAB = OFF_BC + 2 * BSTAGE;
+  static constexpr int OFF_BARS = OFF_SLAB + ((2 * SLAB + 127) / 128) * 128;
   static constexpr int TOTAL = OFF_BARS + 64;
   static constexpr size_t bytes() { return 1024 + TOTAL; }
 };
 
-template <typename T, bool kHasZ>
-__global__ void __launch_bounds__(32, 8) scan_bwd_rl_kernel(const __grid_constant__ RlArgs a) {
+// a lane's 8 items of a per-block tile [rows][8 steps]: fp32 rows are 32 bytes under SWIZZLE_32B (the two 16-byte
+// halves swap when address bit 7 is set, i.e. for rows 4-7 of every 8), 16-bit rows are 16 bytes, unswizzled
+template <typename T>
+__device__ __forceinline__ void lds_blockrow(uint32_t tile_s, int row, float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    const uint32_t base = tile_s + (uint32_t)row * 32u;
+    const uint32_t sw = (uint32_t)((row >> 2) & 1) << 4;
+    unpack16<T>(lds128(base + sw), &v[0]);
+    unpack16<T>(lds128(base + (sw ^ 16u)), &v[4]);
+  } else {
+    unpack16<T>(lds128(tile_s + (uint32_t)row * 16u), &v[0]);
+  }
+}
+
+template <typename T, bool kHasZ, bool kSingle>
+__global__ void __launch_bounds__(32, 12) scan_bwd_rl_kernel(const __grid_constant__ RlArgs a) {
   using Cfg = RlCfg<T>;
   using SM = RlMainSmem<T, kHasZ>;
-  constexpr int NBLK = Cfg::NBLK, ROWT = Cfg::ROWT, BCT = Cfg::BCT;
-  constexpr int ROWS_TX = SM::NROWT * ROWT;
+  constexpr int NBLK = Cfg::NBLK, RB = SM::RB, BB = SM::BB;
+  constexpr int ROWS_TX = SM::NROWT * RB + SM::XB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BARS);  // [0] rows, [1],[2] B/C stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BARS);  // [0],[1] row stages, [2],[3] B/C stages
   const uint32_t smem_s = keep(smem_u32(smem));
   const uint32_t bc_s = smem_s + SM::OFF_BC, slab_s = smem_s + SM::OFF_SLAB;
   const int lane = threadIdx.x;
@@ -253,29 +320,34 @@ __global__ void __launch_bounds__(32, 8) scan_bwd_rl_kernel(const __grid_constan
   const int d0 = g * a.dpg + rb * 32, d = d0 + lane;
   const long rowg = (long)b * a.dim + d;
   const int t_lo = c * a.tpc, t_hi = min(a.ntl, t_lo + a.tpc);
-  const long nbt = a.L / kFine;  // fine blocks per row
+  const int j_lo = t_lo * NBLK, j_hi = t_hi * NBLK;  // fine blocks [j_lo, j_hi), walked last to first
 
-  auto issue_rows = [&](int t) {
-    mbar_arrive_expect_tx(&bars[0], ROWS_TX);
-    tma_load_4d(smem, &a.tm_u, &bars[0], 0, t, d0, b);
-    tma_load_4d(smem + ROWT, &a.tm_delta, &bars[0], 0, t, d0, b);
-    tma_load_4d(smem + 2 * ROWT, &a.tm_dout, &bars[0], 0, t, d0, b);
-    if (kHasZ) tma_load_4d(smem + 3 * ROWT, &a.tm_z, &bars[0], 0, t, d0, b);
+  auto issue_rows = [&](int j, int s) {
+    uint8_t* st = smem + s * SM::RSTAGE;
+    mbar_arrive_expect_tx(&bars[s], ROWS_TX);
+    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, d0, b);
+    tma_load_4d(st + RB, &a.tm_delta, &bars[s], 0, j, d0, b);
+    tma_load_4d(st + 2 * RB, &a.tm_dout, &bars[s], 0, j, d0, b);
+    if (kHasZ) tma_load_4d(st + 3 * RB, &a.tm_z, &bars[s], 0, j, d0, b);
+    // h entering block j = the forward's checkpoint at the end of block j - 1 (block -1 is out of bounds: zero fill)
+    tma_load_4d(st + SM::OFF_XF, &a.tm_xf, &bars[s], 0, j - 1, d0, b);
   };
-  auto issue_bc = [&](int t, int s) {
-    uint8_t* st = smem + SM::OFF_BC + s * 2 * BCT;
-    mbar_arrive_expect_tx(&bars[1 + s], 2 * BCT);
-    tma_load_5d(st, &a.tm_B, &bars[1 + s], 0, t, 0, g, b);
-    tma_load_5d(st + BCT, &a.tm_C, &bars[1 + s], 0, t, 0, g, b);
+  auto issue_bc = [&](int j, int s) {
+    uint8_t* st = smem + SM::OFF_BC + s * SM::BSTAGE;
+    mbar_arrive_expect_tx(&bars[2 + s], SM::BSTAGE);
+    tma_load_5d(st, &a.tm_B, &bars[2 + s], 0, j, 0, g, b);
+    tma_load_5d(st + BB, &a.tm_C, &bars[2 + s], 0, j, 0, g, b);
   };
   if (lane == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init(&bars[2], 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-    issue_rows(t_hi - 1);
-    issue_bc(t_hi - 1, 0);
-    if (t_hi - 2 >= t_lo) issue_bc(t_hi - 2, 1);
+    issue_rows(j_hi - 1, 0);
+    issue_bc(j_hi - 1, 0);
+    if (j_hi - 2 >= j_lo) {
+      issue_rows(j_hi - 2, 1);
+      issue_bc(j_hi - 2, 1);
+    }
   }
   __syncwarp();
   float A2[kMaxState], R[kMaxState], dAacc[kMaxState];
@@ -300,169 +372,209 @@ __global__ void __launch_bounds__(32, 8) scan_bwd_rl_kernel(const __grid_constan
   const uint32_t slab_r0 = keep(slab_s + (uint32_t)(r_arr * SM::SLAB1 + r_q * 288 + r_p * 8));
   const uint32_t slab_r1 = keep(slab_s + (uint32_t)(r_arr * SM::SLAB1 + r_q * 288 + ((r_p * 8) ^ 16)));
   float* dG0 = (r_arr ? a.dC : a.dB) + ((long)b * a.ngroups + g) * kMaxState * a.L + r_p * 2;
-  const bool single = a.single != 0;
+  // h entering the block: lane's 64 bytes of the xf tile, 16-byte pieces swizzled with (row >> 1) & 3 (SWIZZLE_64B)
+  const uint32_t xf_l = keep((uint32_t)SM::OFF_XF + (uint32_t)lane * 64u);
+  const uint32_t xf_key = (uint32_t)((lane >> 1) & 3);
+  const unsigned zero = a.zero;
+  long Lb = a.L * 4;  // byte pitch of a dB / dC state row, kept in vector registers
+  asm volatile("" : "+l"(Lb));
 
   int k = 0;
-  for (int t = t_hi - 1; t >= t_lo; --t, ++k) {
-    const int s = k & 1;
-    mbar_wait(&bars[0], k & 1);
-    mbar_wait(&bars[1 + s], (k >> 1) & 1);
-    const uint32_t tB = bc_s + s * 2 * BCT, tC = tB + BCT;
 #pragma unroll 1
-    for (int blk = NBLK - 1; blk >= 0; --blk) {
-      const long jb = (long)t * NBLK + blk;  // fine block index along L
-      float dl[8], dlu[8], dy[8], uu[8], sB[8], ddl[8];
-      float yv[kHasZ ? 8 : 1], dzf[kHasZ ? 8 : 1];
-      lds_block<T>(smem_s, lane, blk, uu);
-      lds_block<T>(smem_s + ROWT, lane, blk, dl);
-      lds_block<T>(smem_s + 2 * ROWT, lane, blk, dy);
-      if constexpr (kHasZ) {
-        float zz[8];
-        lds_block<T>(smem_s + 3 * ROWT, lane, blk, zz);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float sg = sigmoid_f(zz[i]);
-          dzf[i] = dy[i] * sg * (1.f + zz[i] * (1.f - sg));  // dout * d silu(z)/dz
-          dy[i] = dy[i] * zz[i] * sg;                         // dout * silu(z)
-          yv[i] = Dv * uu[i];
-        }
-      }
-      // h entering the block: the forward's fine checkpoint of the previous block (zero at the sequence start)
-      float4 hq[4];
-      {
-        const float4* xin = reinterpret_cast<const float4*>(a.xf + (rowg * nbt + (jb - 1)) * kMaxState);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) hq[q] = jb > 0 ? __ldg(xin + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+  for (int jb = j_hi - 1; jb >= j_lo; --jb, ++k) {
+    const int s = k & 1;
+    const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+    mbar_wait(&bars[s], ph);
+    const uint32_t rst = smem_s + s * SM::RSTAGE;
+    float dl[8], dlu[8], dy[8], uu[8], sB[8], ddl[8];
+    float yv[kHasZ ? 8 : 1], dzf[kHasZ ? 8 : 1];
+    lds_blockrow<T>(rst, lane, uu);
+    lds_blockrow<T>(rst + RB, lane, dl);
+    lds_blockrow<T>(rst + 2 * RB, lane, dy);
+    if constexpr (kHasZ) {
+      float zz[8];
+      lds_blockrow<T>(rst + 3 * RB, lane, zz);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        float x = dl[i] + bias;
-        if (a.softplus) x = softplus_f(x);
-        dl[i] = x;
-        dlu[i] = x * uu[i];
-        sB[i] = 0.f;
-        ddl[i] = 0.f;
-      }
-      if (blk == 0) {  // the row tiles now live in registers: request the next tile
-        __syncwarp();
-        if (lane == 0 && t - 1 >= t_lo) issue_rows(t - 1);
-      }
-      float* dG = dG0 + jb * kFine;
-
-#pragma unroll
-      for (int n = 0; n < kMaxState; ++n) {
-        const float An = A2[n] * kLn2;
-        const float4 h4 = hq[n >> 2];
-        const float hin = (n & 3) == 0 ? h4.x : (n & 3) == 1 ? h4.y : (n & 3) == 2 ? h4.z : h4.w;
-        float av[8], bv[8], hh[8], cdy[8], dd[8];
-        lds_block<T>(tB, n, blk, bv);
-        lds_block<T>(tC, n, blk, cdy);
-        [[maybe_unused]] float cz[kHasZ ? 8 : 1];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float2 x2 = mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n]));
-          av[2 * kk] = ex2_approx(x2.x);
-          av[2 * kk + 1] = ex2_approx(x2.y);
-          const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
-          hh[2 * kk] = b2.x;  // b_t until the recurrence overwrites it with h_t
-          hh[2 * kk + 1] = b2.y;
-          if constexpr (kHasZ) {
-            cz[2 * kk] = cdy[2 * kk];
-            cz[2 * kk + 1] = cdy[2 * kk + 1];
-          }
-          const float2 c2 = mul2(f2(cdy[2 * kk], cdy[2 * kk + 1]), f2(dy[2 * kk], dy[2 * kk + 1]));
-          cdy[2 * kk] = c2.x;
-          cdy[2 * kk + 1] = c2.y;
-        }
-        // forward recurrence for h, reverse recurrence for dh (independent chains)
-        float bsave[8];
-        float h = hin;
-        float dh = cdy[7] + R[n];
-        dd[7] = dh;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          bsave[i] = hh[i];
-          h = fmaf(av[i], h, hh[i]);
-          hh[i] = h;
-          if (i < 7) {
-            const int j = 6 - i;
-            dh = fmaf(av[j + 1], dh, cdy[j]);
-            dd[j] = dh;
-          }
-        }
-        R[n] = av[0] * dd[0];  // R leaving the block
-        // element-wise products, packed over time pairs
-        float2 gs2 = f2(0.f, 0.f);
-        float vC[8], vB[8];
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float2 h2 = f2(hh[2 * kk], hh[2 * kk + 1]);
-          const float2 d2 = f2(dd[2 * kk], dd[2 * kk + 1]);
-          const float2 c2 = mul2(f2(dy[2 * kk], dy[2 * kk + 1]), h2);  // dC_t[n] of this row
-          vC[2 * kk] = c2.x;
-          vC[2 * kk + 1] = c2.y;
-          const float2 ah2 = sub2(h2, f2(bsave[2 * kk], bsave[2 * kk + 1]));  // a_t h_{t-1}
-          const float2 gq2 = mul2(d2, ah2);
-          float2 ddl2 = f2(ddl[2 * kk], ddl[2 * kk + 1]);
-          ddl2 = fma2(f2(An, An), gq2, ddl2);
-          ddl[2 * kk] = ddl2.x;
-          ddl[2 * kk + 1] = ddl2.y;
-          gs2 = fma2(f2(dl[2 * kk], dl[2 * kk + 1]), gq2, gs2);
-          const float2 b2 = mul2(d2, f2(dlu[2 * kk], dlu[2 * kk + 1]));  // dB_t[n] of this row
-          vB[2 * kk] = b2.x;
-          vB[2 * kk + 1] = b2.y;
-          float2 s2 = f2(sB[2 * kk], sB[2 * kk + 1]);
-          s2 = fma2(d2, f2(bv[2 * kk], bv[2 * kk + 1]), s2);
-          sB[2 * kk] = s2.x;
-          sB[2 * kk + 1] = s2.y;
-          if constexpr (kHasZ) {
-            float2 y2 = f2(yv[2 * kk], yv[2 * kk + 1]);
-            y2 = fma2(f2(cz[2 * kk], cz[2 * kk + 1]), h2, y2);
-            yv[2 * kk] = y2.x;
-            yv[2 * kk + 1] = y2.y;
-          }
-        }
-        dAacc[n] += gs2.x + gs2.y;  // this row's share of dA[n]
-        // ---- dB / dC: reduce the warp's 32 rows through the slab ----
-        sts128(slab_w, vB[0], vB[1], vB[2], vB[3]);
-        sts128(slab_w ^ 16u, vB[4], vB[5], vB[6], vB[7]);
-        sts128(slab_w + SM::SLAB1, vC[0], vC[1], vC[2], vC[3]);
-        sts128((slab_w ^ 16u) + SM::SLAB1, vC[4], vC[5], vC[6], vC[7]);
-        __syncwarp();
-        float2 acc = lds64(slab_r0);
-#pragma unroll
-        for (int i = 1; i < 8; ++i) acc = __fadd2_rn(acc, lds64((i < 4 ? slab_r0 : slab_r1) + i * 32));
-        __syncwarp();
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
-        acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
-        acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
-        if (r_q == 0) stg64_or_red(dG + (long)n * a.L, acc.x, acc.y, single);
-      }
-
-      // ---- per-(row, t) epilogue of the block ----
-      const long tpos = jb * kFine;
-      float outv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) outv[i] = fmaf(dl[i], sB[i], Dv * dy[i]);  // du
-      stg_items<T, 8>(reinterpret_cast<T*>(a.du) + rowg * a.L, outv, tpos, a.L, true);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float gd = fmaf(uu[i], sB[i], ddl[i]);  // d loss / d dl
-        if (a.softplus) gd *= sigmoid_from_softplus(dl[i]);
-        outv[i] = gd;
-        db_acc += gd;
-        dD_acc = fmaf(dy[i], uu[i], dD_acc);
-      }
-      stg_items<T, 8>(reinterpret_cast<T*>(a.ddelta) + rowg * a.L, outv, tpos, a.L, true);
-      if constexpr (kHasZ) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) outv[i] = dzf[i] * yv[i];
-        stg_items<T, 8>(reinterpret_cast<T*>(a.dz) + rowg * a.L, outv, tpos, a.L, true);
+        const float sg = sigmoid_f(zz[i]);
+        dzf[i] = dy[i] * sg * (1.f + zz[i] * (1.f - sg));  // dout * d silu(z)/dz
+        dy[i] = dy[i] * zz[i] * sg;                         // dout * silu(z)
+        yv[i] = Dv * uu[i];
       }
     }
-    __syncwarp();  // every lane is done with B/C stage s
-    if (lane == 0 && t - 2 >= t_lo) issue_bc(t - 2, s);
+    float4 hq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = lds128(rst + xf_l + (((uint32_t)q ^ xf_key) << 4));
+      hq[q] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = dl[i] + bias;
+      if (a.softplus) x = softplus_f(x);
+      dl[i] = x;
+      dlu[i] = x * uu[i];
+      sB[i] = 0.f;
+      ddl[i] = 0.f;
+    }
+    // this stage's row data now lives in registers: request the block after the next one into it
+    __syncwarp();
+    if (lane == 0 && jb - 2 >= j_lo) issue_rows(jb - 2, s);
+    mbar_wait(&bars[2 + s], ph);
+    const uint32_t tB = bc_s + s * SM::BSTAGE, tC = tB + BB;
+    float* dG = dG0 + (long)jb * kFine;
+
+    // The state loop is software-pipelined by hand (the shared-memory helpers are ordered asm, so the order written
+    // here is the order issued): B/C of state n+1 are requested first, the slab of state n-1 is read back before
+    // the recurrences of state n start and summed while they run, and the products of state n go to the other slab.
+    float bcv[2][2][8];  // [buffer][B, C][step]
+    lds_bc<T>(tB, 0, bcv[0][0]);
+    lds_bc<T>(tC, 0, bcv[0][1]);
+    float2 racc[8];
+    char* dGn = reinterpret_cast<char*>(dG);  // dB / dC row of the state being reduced
+    auto slab_load = [&](int buf) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) racc[i] = lds64((i < 4 ? slab_r0 : slab_r1) + i * 32 + buf * SM::SLAB);
+    };
+    // the reduction of the previous state's slab is spread over the current state's work in three steps, each pinned
+    // behind a value the current state produces at that point (order_after)
+    float2 acc;
+    auto slab_sum = [&](float dep) {
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) order_after(racc[i].x, dep, zero);
+      acc = __fadd2_rn(__fadd2_rn(__fadd2_rn(racc[0], racc[1]), __fadd2_rn(racc[2], racc[3])),
+                       __fadd2_rn(__fadd2_rn(racc[4], racc[5]), __fadd2_rn(racc[6], racc[7])));
+    };
+    auto slab_xor = [&](int m, float dep) {
+      order_after(acc.x, dep, zero);
+      const float ox = __shfl_xor_sync(0xffffffffu, acc.x, m), oy = __shfl_xor_sync(0xffffffffu, acc.y, m);
+      acc.x += ox;
+      acc.y += oy;
+    };
+    auto slab_store = [&](float dep) {
+      order_after(acc.x, dep, zero);
+      if (r_q == 0) stg64_or_red(reinterpret_cast<float*>(dGn), acc.x, acc.y, kSingle);
+      dGn += Lb;
+    };
+#pragma unroll
+    for (int n = 0; n < kMaxState; ++n) {
+      float (&bv)[8] = bcv[n & 1][0];
+      float (&cdy)[8] = bcv[n & 1][1];
+      if (n + 1 < kMaxState) {
+        lds_bc<T>(tB, n + 1, bcv[(n + 1) & 1][0]);
+        lds_bc<T>(tC, n + 1, bcv[(n + 1) & 1][1]);
+      }
+      const float An = A2[n] * kLn2;
+      const float4 h4 = hq[n >> 2];
+      const float hin = (n & 3) == 0 ? h4.x : (n & 3) == 1 ? h4.y : (n & 3) == 2 ? h4.z : h4.w;
+      float av[8], hh[8], dd[8];
+      [[maybe_unused]] float cz[kHasZ ? 8 : 1];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 x2 = mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n]));
+        av[2 * kk] = ex2_approx(x2.x);
+        av[2 * kk + 1] = ex2_approx(x2.y);
+        const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
+        hh[2 * kk] = b2.x;  // b_t until the recurrence overwrites it with h_t
+        hh[2 * kk + 1] = b2.y;
+        if constexpr (kHasZ) {
+          cz[2 * kk] = cdy[2 * kk];
+          cz[2 * kk + 1] = cdy[2 * kk + 1];
+        }
+        const float2 c2 = mul2(f2(cdy[2 * kk], cdy[2 * kk + 1]), f2(dy[2 * kk], dy[2 * kk + 1]));
+        cdy[2 * kk] = c2.x;
+        cdy[2 * kk + 1] = c2.y;
+      }
+      if (n > 0) slab_load((n - 1) & 1);
+      // forward recurrence for h, reverse recurrence for dh (independent chains)
+      float bsave[8];
+      float h = hin;
+      float dh = cdy[7] + R[n];
+      dd[7] = dh;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bsave[i] = hh[i];
+        h = fmaf(av[i], h, hh[i]);
+        hh[i] = h;
+        if (i < 7) {
+          const int j = 6 - i;
+          dh = fmaf(av[j + 1], dh, cdy[j]);
+          dd[j] = dh;
+        }
+        if (i == 4 && n > 0) slab_sum(h);
+      }
+      R[n] = av[0] * dd[0];  // R leaving the block
+      if (n > 0) slab_xor(1, hh[7]);
+      // element-wise products, packed over time pairs
+      float2 gs2 = f2(0.f, 0.f);
+      float vC[8], vB[8];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 h2 = f2(hh[2 * kk], hh[2 * kk + 1]);
+        const float2 d2 = f2(dd[2 * kk], dd[2 * kk + 1]);
+        const float2 c2 = mul2(f2(dy[2 * kk], dy[2 * kk + 1]), h2);  // dC_t[n] of this row
+        vC[2 * kk] = c2.x;
+        vC[2 * kk + 1] = c2.y;
+        const float2 ah2 = sub2(h2, f2(bsave[2 * kk], bsave[2 * kk + 1]));  // a_t h_{t-1}
+        const float2 gq2 = mul2(d2, ah2);
+        float2 ddl2 = f2(ddl[2 * kk], ddl[2 * kk + 1]);
+        ddl2 = fma2(f2(An, An), gq2, ddl2);
+        ddl[2 * kk] = ddl2.x;
+        ddl[2 * kk + 1] = ddl2.y;
+        gs2 = fma2(f2(dl[2 * kk], dl[2 * kk + 1]), gq2, gs2);
+        const float2 b2 = mul2(d2, f2(dlu[2 * kk], dlu[2 * kk + 1]));  // dB_t[n] of this row
+        vB[2 * kk] = b2.x;
+        vB[2 * kk + 1] = b2.y;
+        float2 s2 = f2(sB[2 * kk], sB[2 * kk + 1]);
+        s2 = fma2(d2, f2(bv[2 * kk], bv[2 * kk + 1]), s2);
+        sB[2 * kk] = s2.x;
+        sB[2 * kk + 1] = s2.y;
+        if constexpr (kHasZ) {
+          float2 y2 = f2(yv[2 * kk], yv[2 * kk + 1]);
+          y2 = fma2(f2(cz[2 * kk], cz[2 * kk + 1]), h2, y2);
+          yv[2 * kk] = y2.x;
+          yv[2 * kk + 1] = y2.y;
+        }
+        if (kk == 1 && n > 0) slab_xor(2, sB[2]);
+      }
+      if (n > 0) slab_store(sB[6]);
+      dAacc[n] += gs2.x + gs2.y;  // this row's share of dA[n]
+      // ---- dB / dC products of the warp's 32 rows go to slab buffer n & 1 (reduced during state n + 1) ----
+      const uint32_t sw = slab_w + (n & 1) * SM::SLAB;
+      sts128(sw, vB[0], vB[1], vB[2], vB[3]);
+      sts128(sw ^ 16u, vB[4], vB[5], vB[6], vB[7]);
+      sts128(sw + SM::SLAB1, vC[0], vC[1], vC[2], vC[3]);
+      sts128((sw ^ 16u) + SM::SLAB1, vC[4], vC[5], vC[6], vC[7]);
+    }
+    slab_load((kMaxState - 1) & 1);
+    slab_sum(0.f);
+    slab_xor(1, 0.f);
+    slab_xor(2, 0.f);
+    slab_store(0.f);
+    __syncwarp();  // the next block writes slab buffer 0 again; every lane is done with B/C stage s
+    if (lane == 0 && jb - 2 >= j_lo) issue_bc(jb - 2, s);
+
+    // ---- per-(row, t) epilogue of the block ----
+    const long tpos = (long)jb * kFine;
+    float outv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) outv[i] = fmaf(dl[i], sB[i], Dv * dy[i]);  // du
+    stg_items<T, 8>(reinterpret_cast<T*>(a.du) + rowg * a.L, outv, tpos, a.L, true);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float gd = fmaf(uu[i], sB[i], ddl[i]);  // d loss / d dl
+      if (a.softplus) gd *= sigmoid_from_softplus(dl[i]);
+      outv[i] = gd;
+      db_acc += gd;
+      dD_acc = fmaf(dy[i], uu[i], dD_acc);
+    }
+    stg_items<T, 8>(reinterpret_cast<T*>(a.ddelta) + rowg * a.L, outv, tpos, a.L, true);
+    if constexpr (kHasZ) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) outv[i] = dzf[i] * yv[i];
+      stg_items<T, 8>(reinterpret_cast<T*>(a.dz) + rowg * a.L, outv, tpos, a.L, true);
+    }
   }
   // (dim)-shaped sums: over batch and chunks with fp32 atomics
 #pragma unroll
@@ -471,7 +583,155 @@ __global__ void __launch_bounds__(32, 8) scan_bwd_rl_kernel(const __grid_constan
   if (a.dbias) atomicAdd(a.dbias + d, db_acc);
 }
 
+// ================================================================================================
+// Forward main pass (row-per-lane)
+// ================================================================================================
+// Same lane mapping and per-block TMA ring as the backward.  A lane walks its chunk first block to last with all 16
+// states in registers: per state one forward recurrence over the block's 8 steps, y_t += C_t[n] h_t[n] packed over time
+// pairs.  At every block end the 16 states leave as one 64-byte run of the fine checkpoints (free: they sit in
+// registers), every 16th block also as the coarse checkpoint x the C ABI has always returned.
+template <typename T, bool kHasZ>
+struct RlFwdSmem {
+  static constexpr int NROWT = kHasZ ? 3 : 2;                    // u, delta, [z]
+  static constexpr int RB = 32 * kFine * (int)sizeof(T);
+  static constexpr int RSTAGE = ((NROWT * RB + 1023) / 1024) * 1024;
+  static constexpr int BB = kMaxState * kFine * (int)sizeof(T);
+  static constexpr int BSTAGE = ((2 * BB + 1023) / 1024) * 1024;
+  static constexpr int OFF_BC = 2 * RSTAGE, OFF_BARS = OFF_BC + 2 * BSTAGE;
+  static constexpr int TOTAL = OFF_BARS + 64;
+  static constexpr size_t bytes() { return 1024 + TOTAL; }
+};
+
+template <typename T, bool kHasZ>
+__global__ void __launch_bounds__(32, 16) scan_fwd_rl_kernel(const __grid_constant__ RlArgs a) {
+  using SM = RlFwdSmem<T, kHasZ>;
+  constexpr int NBLK = RlCfg<T>::NBLK, RB = SM::RB, BB = SM::BB;
+  constexpr int BPC = NZ_CHUNK / kFine;  // fine blocks per coarse checkpoint
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BARS);  // [0],[1] row stages, [2],[3] B/C stages
+  const uint32_t smem_s = keep(smem_u32(smem));
+  const int lane = threadIdx.x;
+
+  const int item = blockIdx.x;
+  const int c = item % a.nchunks;
+  int w = item / a.nchunks;
+  const int rb = w % a.nrb;
+  w /= a.nrb;
+  const int g = w % a.ngroups, b = w / a.ngroups;
+  const int d0 = g * a.dpg + rb * 32, d = d0 + lane;
+  const long rowg = (long)b * a.dim + d;
+  const int t_lo = c * a.tpc, t_hi = min(a.ntl, t_lo + a.tpc);
+  const int j_lo = t_lo * NBLK, j_hi = t_hi * NBLK;
+  const long nbt = a.L / kFine;
+
+  auto issue = [&](int j, int s) {
+    uint8_t* st = smem + s * SM::RSTAGE;
+    mbar_arrive_expect_tx(&bars[s], SM::NROWT * RB);
+    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, d0, b);
+    tma_load_4d(st + RB, &a.tm_delta, &bars[s], 0, j, d0, b);
+    if (kHasZ) tma_load_4d(st + 2 * RB, &a.tm_z, &bars[s], 0, j, d0, b);
+    uint8_t* sb = smem + SM::OFF_BC + s * SM::BSTAGE;
+    mbar_arrive_expect_tx(&bars[2 + s], 2 * BB);
+    tma_load_5d(sb, &a.tm_B, &bars[2 + s], 0, j, 0, g, b);
+    tma_load_5d(sb + BB, &a.tm_C, &bars[2 + s], 0, j, 0, g, b);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    issue(j_lo, 0);
+    if (j_lo + 1 < j_hi) issue(j_lo + 1, 1);
+  }
+  __syncwarp();
+  float A2[kMaxState], h[kMaxState];
+  {
+    const float* hin = a.Rin + (rowg * a.nchunks + c) * kMaxState;
+#pragma unroll
+    for (int n = 0; n < kMaxState; ++n) {
+      A2[n] = __ldg(a.A + (long)d * a.A_ds + n) * kLog2e;
+      h[n] = a.nchunks > 1 ? __ldg(hin + n) : 0.f;
+    }
+  }
+  const float Dv = a.D ? __ldg(a.D + d) : 0.f;
+  const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
+  const long orow = (long)b * a.o_bs + (long)d * a.o_ds;
+
+  int k = 0;
+#pragma unroll 1
+  for (int jb = j_lo; jb < j_hi; ++jb, ++k) {
+    const int s = k & 1;
+    const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+    mbar_wait(&bars[s], ph);
+    const uint32_t rst = smem_s + s * SM::RSTAGE;
+    float dl[8], dlu[8], y[8];
+    [[maybe_unused]] float zz[kHasZ ? 8 : 1];
+    lds_blockrow<T>(rst, lane, dlu);  // u for now
+    lds_blockrow<T>(rst + RB, lane, dl);
+    if constexpr (kHasZ) lds_blockrow<T>(rst + 2 * RB, lane, zz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = dl[i] + bias;
+      if (a.softplus) x = softplus_f(x);
+      dl[i] = x;
+      y[i] = Dv * dlu[i];
+      dlu[i] = x * dlu[i];
+    }
+    mbar_wait(&bars[2 + s], ph);
+    const uint32_t tB = smem_s + SM::OFF_BC + s * SM::BSTAGE, tC = tB + BB;
+#pragma unroll
+    for (int n = 0; n < kMaxState; ++n) {
+      float bv[8], cv[8], hh[8];
+      lds_bc<T>(tB, n, bv);
+      lds_bc<T>(tC, n, cv);
+      float hc = h[n];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 x2 = mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n]));
+        const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
+        hc = fmaf(ex2_approx(x2.x), hc, b2.x);
+        hh[2 * kk] = hc;
+        hc = fmaf(ex2_approx(x2.y), hc, b2.y);
+        hh[2 * kk + 1] = hc;
+      }
+      h[n] = hc;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float2 y2 = f2(y[2 * kk], y[2 * kk + 1]);
+        y2 = fma2(f2(cv[2 * kk], cv[2 * kk + 1]), f2(hh[2 * kk], hh[2 * kk + 1]), y2);
+        y[2 * kk] = y2.x;
+        y[2 * kk + 1] = y2.y;
+      }
+    }
+    // every lane is done with this block's stages: request the block after the next one
+    __syncwarp();
+    if (lane == 0 && jb + 2 < j_hi) issue(jb + 2, s);
+    if constexpr (kHasZ) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] *= zz[i] * sigmoid_f(zz[i]);
+    }
+    const long tpos = (long)jb * kFine;
+    if (sizeof(T) == 2 && a.out_f32)
+      stg_items<float, 8>(reinterpret_cast<float*>(a.out) + orow, y, tpos, a.L, true);
+    else
+      stg_items<T, 8>(reinterpret_cast<T*>(a.out) + orow, y, tpos, a.L, true);
+    // checkpoints: h at the end of the block
+    if (a.xfw) {
+      float4* xo = reinterpret_cast<float4*>(a.xfw + (rowg * nbt + jb) * kMaxState);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xo[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    }
+    if ((jb + 1) % BPC == 0 || jb + 1 == nbt) {
+      float4* xo = reinterpret_cast<float4*>(a.x + (rowg * a.nck + jb / BPC) * kMaxState);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xo[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    }
+  }
+}
+
 template <typename T>
 cudaError_t launch_scan_bwd_rl(const RlArgs& a, bool has_z, cudaStream_t stream);
+template <typename T>
+cudaError_t launch_scan_fwd_rl(const RlArgs& a, bool has_z, cudaStream_t stream);
 
 }  // namespace nz

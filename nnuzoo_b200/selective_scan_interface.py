@@ -70,7 +70,7 @@ def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, forc
     # (the caching allocator orders its reuse after this stream's launches)
     # (the _cp size lets few-rows / long-L forwards run chunk-parallel; it equals the base size for other shapes)
     nbytes = _native.workspace_bytes(batch, dim)
-    if forward and L >= 4096:
+    if forward:
         nbytes = max(nbytes, int(_native.lib().nz_scan_workspace_bytes_cp(ctypes.byref(desc))))
     if xf is not None:  # backward with fine checkpoints: room for the chunk aggregates of the row-per-lane kernels
         desc.xf = _ptr(xf)
