@@ -340,6 +340,15 @@ static bool rl_shape_ok(const NzScanDesc* d) {
   if (!d || d->batch < 1 || d->dim < 1 || d->ngroups < 1 || d->seqlen < 1 || d->dim % d->ngroups) return false;
   if (d->force_generic || d->dstate != NZ_MAX_DSTATE || (d->dim / d->ngroups) % 32 != 0) return false;
   if (getenv("NZ_NO_RL")) return false;
+  // Measured old (warp-scan, chained) vs row-per-lane over the M2Net shapes (profiles/r02_rl_table.log): the
+  // row-per-lane backward wins from about 25 M elements up (-8 .. -21 %) and is the only chunk-parallel backward
+  // (batch-1 inference shape 3.8 -> 1.4 ms); below that its three launches and the aggregate pass cost more than they
+  // save (12 x 128 x 4096: 0.27 vs 0.19 ms).
+  {
+    long min_elts = 24L << 20;
+    if (const char* e = getenv("NZ_RL_MIN_ELTS")) min_elts = atol(e);  // tests / tuning
+    if ((long)d->batch * d->dim * d->seqlen < min_elts) return false;
+  }
   const int64_t rd[2] = {d->dim, d->batch};
   const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
   const int64_t ds[2] = {d->delta_stride[1], d->delta_stride[0]};
@@ -356,14 +365,15 @@ static bool rl_shape_ok(const NzScanDesc* d) {
 }
 
 // Chunks along L: (row block, chunk) work items are one warp each and 8 warps are resident per SM; all items cost the
-// same, so the launch is cut into about 8 waves of them (two full waves plus 32 stragglers measured 2.14 ms where 1.43
-// would do: profiles/r02_kernel_tuning.md), each chunk a whole number of 128-byte tiles.
-static void rl_plan(const NzScanDesc* d, int* nchunks, int* tpc) {
+// same, so the launch is cut into about 6 waves of them (two full waves plus 32 stragglers measured 2.14 ms where 1.43
+// would do: profiles/r02_kernel_tuning.md), each chunk a whole number of 128-byte tiles.  `resident` = warps per SM of
+// the main pass (backward 12, forward 16).
+static void rl_plan(const NzScanDesc* d, int* nchunks, int* tpc, int resident = 12) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long rbt = (long)d->batch * (d->dim / 32);
   const long ntl = d->seqlen * (long)esize(d->dtype) / 128;
-  long target = 8L * sms * 8;
+  long target = 6L * sms * resident;
   if (const char* e = getenv("NZ_RL_ITEMS")) target = atol(e);  // tuning override
   long nc = (target + rbt - 1) / rbt;
   if (nc < 1) nc = 1;
@@ -375,7 +385,7 @@ static void rl_plan(const NzScanDesc* d, int* nchunks, int* tpc) {
 
 static int64_t rl_extra_bytes(const NzScanDesc* d) {
   int nc = 1, tpc = 1;
-  rl_plan(d, &nc, &tpc);
+  rl_plan(d, &nc, &tpc, 16);  // the forward's plan has the most chunks
   if (nc <= 1) return 0;
   const int64_t one = (((int64_t)d->batch * d->dim * nc * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
   return 3 * one;
@@ -468,7 +478,7 @@ static cudaError_t run_fwd_rl(const NzScanDesc* d, cudaStream_t st) {
   r.batch = d->batch; r.dim = d->dim; r.ngroups = d->ngroups; r.dpg = d->dim / d->ngroups;
   r.nrb = r.dpg / 32;
   r.ntl = (int)(L * (int64_t)esize(d->dtype) / 128);
-  rl_plan(d, &r.nchunks, &r.tpc);
+  rl_plan(d, &r.nchunks, &r.tpc, 16);
   r.softplus = d->delta_softplus;
   if (r.nchunks > 1) {
     const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
@@ -483,7 +493,16 @@ static cudaError_t run_fwd_rl(const NzScanDesc* d, cudaStream_t st) {
 }
 
 static bool rl_fwd_usable(const NzScanDesc* d) {
-  if (getenv("NZ_NO_RL_FWD") || !rl_shape_ok(d)) return false;
+  // Measured (profiles/r02_rl_table.log): without fine checkpoints the warp-scan forward is as fast or faster on every
+  // shape; with them (training) this one wins while a row is at most 256 KB (12 x 128 x 65536: 1.16 vs 1.35 ms,
+  // 12 x 256 x 65536: 2.21 vs 2.46) and loses beyond (12 x 128 x 262144: 5.71 vs 5.34 ms: its 32-byte boxes at a 1 MB
+  // row pitch).  NZ_RL_FWD=0 / 1 forces the choice.
+  if (!rl_shape_ok(d)) return false;
+  if (const char* on = getenv("NZ_RL_FWD")) {
+    if (atoi(on) == 0) return false;
+  } else if (!d->xf || d->seqlen * (int64_t)esize(d->dtype) > (256 << 10)) {
+    return false;
+  }
   const size_t eo = (d->out_f32 && d->dtype != NZ_F32) ? 4 : esize(d->dtype);
   return aligned16(d->out) && (d->out_stride[0] * eo) % 16 == 0 && (d->out_stride[1] * eo) % 16 == 0 &&
          (!d->xf || aligned16(d->xf)) && aligned16(d->x) &&

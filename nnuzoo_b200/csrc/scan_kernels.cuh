@@ -60,6 +60,9 @@
 #ifndef NZ_BWD_REDUCE_LATE
 #define NZ_BWD_REDUCE_LATE 1  // reduce slab(n-1) 0: after the scans of state n, 1: before writing slab(n) (7.62 -> 7.27), 2: after it
 #endif
+#ifndef NZ_FWD_FINE_DIRECT
+#define NZ_FWD_FINE_DIRECT 0  // fine checkpoints: 1 = one 4-byte store per (block, state), 0 = staged 16-byte vectors
+#endif
 #ifndef NZ_BWD_KEEPB
 #define NZ_BWD_KEEPB 0  // 1: keep B_t[n] in registers instead of re-reading the tile for sum_n dh*B (costs 8 registers)
 #endif
@@ -642,8 +645,19 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
 #endif
       }
       if constexpr (kFineCk) {
-        // h at the end of each 8-step block of the lane's segment -> xf[row][block][state]; four states are gathered
-        // through a lane-private staging column so that the store is one 16-byte vector per block
+        // h at the end of each 8-step block of the lane's segment -> xf[row][block][state]
+#if NZ_FWD_FINE_DIRECT
+        // one 4-byte store per (block, state): the 16 states of a block fill two sectors over 16 trips (merged in L2)
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+          for (int bk = 0; bk < M / NZ_FINE; ++bk) {
+            const long blkg = (long)c * (TL / NZ_FINE) + sl * (M / NZ_FINE) + bk;
+            if (blkg < a.nbt) a.xf[(rowg * a.nbt + blkg) * kMaxState + n + qi] = bv[qi][bk * NZ_FINE + NZ_FINE - 1];
+          }
+        }
+#else
+        // four states are gathered through a lane-private staging column so that the store is one 16-byte vector per block
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) {
           const int nn = n + qi;
@@ -660,6 +674,7 @@ __global__ void __launch_bounds__(WARPS * 32, (kHasZ && sizeof(T) == 4 && M * LP
             }
           }
         }
+#endif
       }
 #pragma unroll
       for (int qi = 0; qi < NQ; ++qi) {

@@ -62,6 +62,48 @@ struct alignas(64) RlArgs {
   unsigned zero; // always 0 (see order_after)
 };
 
+// ---- exp2 on the FMA pipe ----
+// The aggregate passes and the forward main pass are bound by the MUFU pipe (16 ex2 per element at 16 lanes/clk/SM:
+// 90 % busy, issue slots half idle).  A share of the states therefore computes a_t = 2^x with FMA-pipe instructions, two
+// steps at a time: round-to-nearest split x = i + f (magic-number add), degree-5 polynomial for 2^f on [-0.5, 0.5]
+// (max relative error 1.9e-7, the same order as ex2.approx), exponent add by integer arithmetic.  |x| <= 126 is the
+// caller's business (the kernels clamp dl once per block so that |A * dl| * log2(e) <= 126; beyond that a_t is 0 to
+// fp32 anyway).  MEASURED AND SWITCHED OFF (profiles/r02_kernel_tuning.md): with 5 of 16 states on the polynomial the
+// aggregate pass went from 0.454 to 0.49 ms -- MUFU 90 -> 61 %, FMA 34 -> 53 %, issue 54 -> 59 %: at 2-3 resident warps
+// per scheduler the pass is then bound by dependent-issue latency, not by either pipe.  Kept as a build switch.
+#ifndef NZ_RL_POLY_AGG
+#define NZ_RL_POLY_AGG 0   // aggregate passes: states with n % NZ_RL_POLY_AGG == 1 use the polynomial (0: none)
+#endif
+#ifndef NZ_RL_POLY_FWD
+#define NZ_RL_POLY_FWD 0   // forward main pass: states with n % NZ_RL_POLY_FWD == 1
+#endif
+__host__ __device__ constexpr bool rl_poly_state(int n, int mod) { return mod > 0 && n % mod == 1; }
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.f, 12582912.f);
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 i = __fadd2_rn(t, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __fadd2_rn(x, make_float2(-i.x, -i.y));
+  float2 p = make_float2(0.001326472731307149f, 0.001326472731307149f);
+  p = __ffma2_rn(p, f, make_float2(0.009671512991189957f, 0.009671512991189957f));
+  p = __ffma2_rn(p, f, make_float2(0.05550733581185341f, 0.05550733581185341f));
+  p = __ffma2_rn(p, f, make_float2(0.24022242426872253f, 0.24022242426872253f));
+  p = __ffma2_rn(p, f, make_float2(0.6931470036506653f, 0.6931470036506653f));
+  p = __ffma2_rn(p, f, make_float2(1.f, 1.f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+// a_t for a time pair: MUFU or polynomial (`poly` is a compile-time constant after the state loop is unrolled)
+__device__ __forceinline__ float2 ex2_pair(bool poly, float2 x) {
+  if (poly) return ex2_poly2(x);
+  return make_float2(ex2_approx(x.x), ex2_approx(x.y));
+}
+
+#ifndef NZ_RL_BWD_MINB
+#define NZ_RL_BWD_MINB 12  // resident warps per SM the backward main pass is compiled for (register cap 65536 / 32 / MINB)
+#endif
+
 template <typename T>
 struct RlCfg {
   static constexpr int ES = sizeof(T);
@@ -177,6 +219,10 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
   }
   const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
   float dlsum = 0.f;
+  float amax = 0.f;
+#pragma unroll
+  for (int n = 0; n < kMaxState; ++n) amax = fmaxf(amax, fabsf(A2[n]));
+  const float dlim = 126.f / fmaxf(amax, 1e-30f);  // |A2 * dl| <= 126 for the exponent arithmetic of ex2_poly2
 
   for (int k = 0; k < nt; ++k) {
     const int s = k & 1;
@@ -198,21 +244,28 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
       for (int i = 0; i < 8; ++i) {
         float x = dl[i] + bias;
         if (a.softplus) x = softplus_f(x);
-        dl[i] = x;
         dlsum += x;
         if (kFwd) dy[i] *= x;  // dl_t u_t
+        dl[i] = fminf(fmaxf(x, -dlim), dlim);
       }
 #pragma unroll
       for (int n = 0; n < kMaxState; ++n) {
         float cv[8];
         lds_block<T>(st + NROW * ROWT, n, blk, cv);
+        float av[8];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float2 e2 = ex2_pair(rl_poly_state(n, NZ_RL_POLY_AGG), mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n])));
+          av[2 * kk] = e2.x;
+          av[2 * kk + 1] = e2.y;
+        }
         float r = R[n];
         if constexpr (kFwd) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) r = fmaf(ex2_approx(A2[n] * dl[i]), r, cv[i] * dy[i]);  // h_t = a_t h_{t-1} + b_t
+          for (int i = 0; i < 8; ++i) r = fmaf(av[i], r, cv[i] * dy[i]);  // h_t = a_t h_{t-1} + b_t
         } else {
 #pragma unroll
-          for (int i = 7; i >= 0; --i) r = ex2_approx(A2[n] * dl[i]) * fmaf(cv[i], dy[i], r);  // R_{t-1} = a_t (C_t dy_t + R_t)
+          for (int i = 7; i >= 0; --i) r = av[i] * fmaf(cv[i], dy[i], r);  // R_{t-1} = a_t (C_t dy_t + R_t)
         }
         R[n] = r;
       }
@@ -299,7 +352,7 @@ __device__ __forceinline__ void lds_blockrow(uint32_t tile_s, int row, float (&v
 }
 
 template <typename T, bool kHasZ, bool kSingle>
-__global__ void __launch_bounds__(32, 12) scan_bwd_rl_kernel(const __grid_constant__ RlArgs a) {
+__global__ void __launch_bounds__(32, NZ_RL_BWD_MINB) scan_bwd_rl_kernel(const __grid_constant__ RlArgs a) {
   using Cfg = RlCfg<T>;
   using SM = RlMainSmem<T, kHasZ>;
   constexpr int NBLK = Cfg::NBLK, RB = SM::RB, BB = SM::BB;
@@ -656,6 +709,10 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_rl_kernel(const __grid_consta
   const float Dv = a.D ? __ldg(a.D + d) : 0.f;
   const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
   const long orow = (long)b * a.o_bs + (long)d * a.o_ds;
+  float amax = 0.f;
+#pragma unroll
+  for (int n = 0; n < kMaxState; ++n) amax = fmaxf(amax, fabsf(A2[n]));
+  const float dlim = 126.f / fmaxf(amax, 1e-30f);  // |A2 * dl| <= 126 for the exponent arithmetic of ex2_poly2
 
   int k = 0;
 #pragma unroll 1
@@ -673,9 +730,9 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_rl_kernel(const __grid_consta
     for (int i = 0; i < 8; ++i) {
       float x = dl[i] + bias;
       if (a.softplus) x = softplus_f(x);
-      dl[i] = x;
       y[i] = Dv * dlu[i];
       dlu[i] = x * dlu[i];
+      dl[i] = fminf(fmaxf(x, -dlim), dlim);  // from here on dl only feeds the exponents
     }
     mbar_wait(&bars[2 + s], ph);
     const uint32_t tB = smem_s + SM::OFF_BC + s * SM::BSTAGE, tC = tB + BB;
@@ -687,11 +744,11 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_rl_kernel(const __grid_consta
       float hc = h[n];
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        const float2 x2 = mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n]));
+        const float2 e2 = ex2_pair(rl_poly_state(n, NZ_RL_POLY_FWD), mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n])));
         const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
-        hc = fmaf(ex2_approx(x2.x), hc, b2.x);
+        hc = fmaf(e2.x, hc, b2.x);
         hh[2 * kk] = hc;
-        hc = fmaf(ex2_approx(x2.y), hc, b2.y);
+        hc = fmaf(e2.y, hc, b2.y);
         hh[2 * kk + 1] = hc;
       }
       h[n] = hc;

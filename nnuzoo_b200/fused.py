@@ -27,6 +27,10 @@ class _InnerCtx:
 
     saved_tensors = ()
 
+    def __init__(self, needs_grad: bool = True):
+        # SelectiveScanFn.forward asks for fine checkpoints only when some gradient will be wanted
+        self.needs_input_grad = (needs_grad,) * 11
+
     def save_for_backward(self, *tensors):
         self.saved_tensors = tensors
 
@@ -46,7 +50,7 @@ class SS2DCoreFn(torch.autograd.Function):
             raise ValueError("ss2d_core: xs must be (B, 4, D, H*W)")
         if z.shape != (bsz, H, W, D) or z.stride(3) != 1 or z.stride(1) != W * z.stride(2) or z.dtype not in _DT:
             raise ValueError("ss2d_core: z must be a (B, H, W, D) tensor with unit channel stride and collapsible H, W")
-        inner = _InnerCtx()
+        inner = _InnerCtx(any(ctx.needs_input_grad[:8]))
         scan_out = torch.float32 if xs.dtype != torch.float32 else None
         out_y = SelectiveScanFn.forward(inner, xs.view(bsz, K * D, L), dts.view(bsz, K * D, L), As, Bs, Cs, Ds, None,
                                         dt_bias, True, False, scan_out)

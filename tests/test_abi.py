@@ -41,6 +41,28 @@ def test_struct_mirror_matches_the_compiled_layout():
     assert lib.nz_scan_workspace_bytes(ctypes.byref(d)) == _native.workspace_bytes(3, 40)
 
 
+def test_row_per_lane_abi_queries():
+    """nz_scan_fine_bytes / nz_scan_workspace_bytes_bwd / nz_scan_bwd_overwrites_dbc are pure host logic."""
+    from nnuzoo_b200 import _native
+    lib = _native.lib()
+    d = _native.NzScanDesc()
+    d.batch, d.dim, d.dstate, d.ngroups, d.seqlen, d.dtype = 12, 128, 16, 4, 65536, 0
+    d.u = d.delta = d.B = d.C = 256
+    for st in (d.u_stride, d.delta_stride):
+        st[0], st[1] = 128 * 65536, 65536
+    for st in (d.B_stride, d.C_stride):
+        st[0], st[1], st[2] = 4 * 16 * 65536, 16 * 65536, 65536
+    assert lib.nz_scan_fine_bytes(ctypes.byref(d)) == 12 * 128 * (65536 // 8) * 16 * 4
+    assert lib.nz_scan_bwd_overwrites_dbc(ctypes.byref(d)) == 0       # warp-scan backward, 32 rows per group: atomics
+    d.xf = 256
+    assert lib.nz_scan_bwd_overwrites_dbc(ctypes.byref(d)) == 1       # row-per-lane, one warp per group
+    assert lib.nz_scan_workspace_bytes_bwd(ctypes.byref(d)) > lib.nz_scan_workspace_bytes(ctypes.byref(d))
+    d.ngroups = 16                                                    # 8 rows per group: not eligible
+    d.xf = None
+    assert lib.nz_scan_fine_bytes(ctypes.byref(d)) == 0
+    assert lib.nz_scan_bwd_overwrites_dbc(ctypes.byref(d)) == 1       # warp-scan backward, <= 16 rows per group
+
+
 def test_invalid_descriptors_are_rejected_with_a_message():
     from nnuzoo_b200 import _native
     lib = _native.lib()

@@ -60,5 +60,6 @@ def test_fused_path_is_actually_taken():
     n0 = _native.launch_count()
     mod(x)
     plain_launches = _native.launch_count() - n0
-    # fused: dwconv, cross_scan, scan, epilogue = 4; op by op: dwconv, cross_scan, scan, merge, layernorm = 5
-    assert (fused_launches, plain_launches) == (4, 5)
+    # fused: dwconv, cross_scan, scan, epilogue; op by op: dwconv, cross_scan, scan, merge, layernorm -- one launch more
+    # (the scan itself is 1 launch, or 3 when it runs chunk-parallel: aggregate pass, combine, main pass)
+    assert fused_launches >= 4 and plain_launches - fused_launches == 1

@@ -68,12 +68,14 @@ def run_stage(stage):
         print(json.dumps({"tma z bf16": scan_case((2, 16, 1, 16, 512, True), False, True, "bfloat16")}))
         print(json.dumps({"tma z f16": scan_case((2, 16, 1, 16, 512, True), False, True, "float16")}))
     elif stage == "rl":  # row-per-lane backward: one warp per group / several warps per group (RED) / chunked
+        os.environ["NZ_RL_MIN_ELTS"] = "0"
         print(json.dumps({"rl single (2,128,4,16,1024)": scan_case((2, 128, 4, 16, 1024, False), False, True)}))
         print(json.dumps({"rl red (2,128,2,16,4128)": scan_case((2, 128, 2, 16, 4128, False), False, True)}))
         os.environ["NZ_RL_ITEMS"] = "1"
         print(json.dumps({"rl one chunk (2,128,4,16,1024)": scan_case((2, 128, 4, 16, 1024, False), False, True)}))
         del os.environ["NZ_RL_ITEMS"]
     elif stage == "rl_z_16bit":
+        os.environ["NZ_RL_MIN_ELTS"] = "0"
         print(json.dumps({"rl z fp32": scan_case((2, 64, 1, 16, 2048, True), False, True)}))
         print(json.dumps({"rl z bf16": scan_case((2, 64, 1, 16, 2048, True), False, True, "bfloat16")}))
         print(json.dumps({"rl f16": scan_case((2, 64, 2, 16, 2048, False), False, True, "float16")}))
