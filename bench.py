@@ -105,13 +105,15 @@ class ClockSampler:
 
 
 def traffic_per_launch():
-    """Average DRAM bytes (read + write) per scan_bwd launch of this workload, from the committed ncu
-    capture of the same command (profiles/r01_bwd_traffic.json, written by tools/ncu_traffic.py)."""
+    """Average DRAM bytes (read + write) per nz_scan_bwd call of this workload (all the launches of the call), from the
+    committed ncu capture of the same command (profiles/r02_bwd_traffic.json, written by tools/ncu_traffic.py, stamped
+    with the git revision it was taken at)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_bwd_traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
+        with open(os.path.join(ROOT, "profiles", "r02_bwd_traffic.json")) as f:
+            j = json.load(f)
+            return float(j["dram_bytes_per_launch"]), j.get("git")
     except Exception:
-        return None
+        return None, None
 
 
 def measured_peak():
@@ -125,46 +127,75 @@ def measured_peak():
 # -------------------------------------------------------------------------------------------------
 # CPU arm: the reference's own CPU path on a bounded sample of the workload
 # -------------------------------------------------------------------------------------------------
+CFG0 = dict(batch=2, K=4, D=192, N=16, L=64 * 64, R=6)  # BASELINE.json configs[0]; R = dt_rank of d_model 96
+
+
+def cfg0_tensors(device="cpu", seed=0):
+    """BASELINE.md section 4 / SURVEY.md 8(d) inputs of configs[0]: B, C are the split views SS2D hands over."""
+    import math
+
+    import torch
+    c = CFG0
+    kd = c["K"] * c["D"]
+    g = torch.Generator().manual_seed(seed)
+    u = torch.randn(c["batch"], kd, c["L"], generator=g)
+    delta = 0.5 * torch.randn(c["batch"], kd, c["L"], generator=g)
+    A = -torch.arange(1, c["N"] + 1).float().repeat(kd, 1).contiguous()
+    xdbl = torch.randn(c["batch"], c["K"], c["R"] + 2 * c["N"], c["L"], generator=g)
+    dt = torch.exp(torch.rand(kd, generator=g) * (math.log(0.1) - math.log(0.001)) + math.log(0.001))
+    bias = dt + torch.log(-torch.expm1(-dt))          # m2net.py:128-135
+    D = torch.ones(kd)                                # m2net.py:161
+    xdbl = xdbl.to(device)
+    Bv, Cv = xdbl[:, :, c["R"]:c["R"] + c["N"]], xdbl[:, :, c["R"] + c["N"]:]
+    return [t.to(device) for t in (u, delta, A)] + [Bv, Cv] + [t.to(device) for t in (D, bias)]
+
+
 def cpu_sample_run(steps: int, warmup: int):
-    """fwd+bwd of one workload scan at reduced size through the torch port of selective_scan_ref."""
+    """the reference's CPU path on configs[0] (B=2, K=4, D=192, N=16, L=4096, fp32, z=None,
+    delta_softplus, delta_bias), FORWARD ONLY, all host threads.  /root/reference is not on the GPU box, so the
+    function timed is the restatement oracle/torch_port.py of selective_scan_ref (same Python loop of torch ops over L,
+    pinned to the verbatim reference by tests/golden): kind "port", labelled "restated"."""
+    import platform
+
     import torch
 
     from oracle.torch_port import selective_scan_port
 
     torch.set_num_threads(os.cpu_count() or 1)
-    batch, kd, L = 1, 128, 128 * 128  # the stage-1 (K*D = 128) scan of the workload at its 128x128 level
-    g = torch.Generator().manual_seed(0)
-    u = torch.randn(batch, kd, L, generator=g, requires_grad=True)
-    delta = (0.5 * torch.randn(batch, kd, L, generator=g)).requires_grad_(True)
-    A = (-torch.arange(1, N_STATE + 1).float().repeat(kd, 1)).requires_grad_(True)
-    B = torch.randn(batch, K_DIR, N_STATE, L, generator=g, requires_grad=True)
-    C = torch.randn(batch, K_DIR, N_STATE, L, generator=g, requires_grad=True)
-    D = torch.ones(kd, requires_grad=True)
-    bias = torch.full((kd,), -2.0, requires_grad=True)
-    gout = torch.randn(batch, kd, L, generator=g)
+    u, delta, A, Bv, Cv, D, bias = cfg0_tensors("cpu")
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        out = selective_scan_port(u, delta, A, B, C, D, None, bias, True)
-        out.backward(gout)
-        times.append(time.perf_counter() - t0)
-        for t in (u, delta, A, B, C, D, bias):
-            t.grad = None
-    t = sum(times[warmup:]) / max(1, steps)
-    nbytes = scan_bytes(batch, kd, L)["total"]
+    with torch.no_grad():
+        for _ in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = selective_scan_port(u, delta, A, Bv, Cv, D, None, bias, True)
+            times.append(time.perf_counter() - t0)
+    assert bool(torch.isfinite(out).all())
+    ts = sorted(times[warmup:])
+    t = ts[len(ts) // 2]
+    c = CFG0
+    nbytes = scan_bytes(c["batch"], c["K"] * c["D"], c["L"])["fwd"]
+    cpu_model = platform.processor() or platform.machine()
+    try:
+        with open("/proc/cpuinfo") as f:
+            cpu_model = next(l.split(":", 1)[1].strip() for l in f if l.startswith("model name"))
+    except Exception:
+        pass
     return dict(seconds=t, gbps=nbytes / t / 1e9, cores=torch.get_num_threads(),
-                sample=f"selective_scan_ref port (oracle/torch_port.py) fwd+bwd, one stage-1 scan of the workload "
-                       f"at batch {batch}, K*D={kd}, L={L} fp32 ({nbytes / 1e6:.1f} MB algorithmic)")
+                sample=f"configs[0] forward only (B=2, K=4, D=192, N=16, L=4096, fp32, split-view B/C): selective_scan_ref "
+                       f"restated in oracle/torch_port.py, {torch.get_num_threads()} threads on {cpu_model}; median of "
+                       f"{steps} after {warmup} warm-up; {nbytes / 1e6:.1f} MB algorithmic (4(3E+2S))")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_sample_run(args.steps, 1)  # one CPU warm-up pass is enough; each pass takes seconds
+    r = cpu_sample_run(max(1, min(args.steps, 3)), 1)  # one warm-up pass; each pass takes seconds
     line = {
         "impl": "reference", "metric": METRIC, "value": r["gbps"], "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": 1, "ms_per_step": r["seconds"] * 1e3,
+        "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": r["seconds"] * 1e3,
+        "note": "CPU arm as BASELINE.md section 4 fixes it: configs[0], forward only, restated selective_scan_ref; the GPU "
+                "arm's line carries the same shape under configs.cfg0 (fwd and fwd+bwd) next to the configs[1] headline",
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": CONFIG,
         "cpu_baseline": {"value": r["gbps"], "unit": "GB/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
@@ -213,11 +244,6 @@ class Workload:
         self.pool_mult = 2  # operand pools are 2x the largest scan so slices rotate
         g = torch.Generator(device=dev).manual_seed(1234 + dev.index)
         rnd = lambda n, scale=1.0: torch.randn(n, device=dev, generator=g) * scale  # noqa: E731
-        self.u = rnd(kd_max_elems * self.pool_mult)
-        self.delta = rnd(kd_max_elems * self.pool_mult, 0.5)
-        self.dout = rnd(kd_max_elems * self.pool_mult)
-        self.Bm = rnd(bc_max * self.pool_mult)
-        self.Cm = rnd(bc_max * self.pool_mult)
         self.out = torch.empty(kd_max_elems, device=dev)
         self.du = torch.empty(kd_max_elems, device=dev)
         self.dd = torch.empty(kd_max_elems, device=dev)
@@ -233,16 +259,43 @@ class Workload:
         ck = self.native.NZ_CHUNK
         nch_max = max(BATCH * kd * ((L + ck - 1) // ck) * N_STATE for kd, L in self.scans)
         self.x = torch.empty(nch_max, device=dev)
-        self.ws = torch.empty(self.native.workspace_bytes(BATCH, kdm), dtype=torch.uint8, device=dev)
+        # fine checkpoints (h every 8 steps) for the scans the row-per-lane backward takes, and the scratch both
+        # directions need (tile tickets / carries, chunk aggregates): sized once for the largest scan
+        fine_max, ws_max = 0, self.native.workspace_bytes(BATCH, kdm)
+        self.u = self.delta = self.Bm = self.Cm = torch.empty(64, device=dev)  # aligned stand-ins for the size queries
+        for kd, L in self.scans:
+            d = self._bare_desc(kd, L)
+            nfine = int(self.lib.nz_scan_fine_bytes(ctypes.byref(d)))
+            fine_max = max(fine_max, nfine)
+            if nfine:
+                d.xf = ctypes.c_void_p(256)
+            ws_max = max(ws_max, int(self.lib.nz_scan_workspace_bytes_bwd(ctypes.byref(d))),
+                         int(self.lib.nz_scan_workspace_bytes_cp(ctypes.byref(d))))
+        self.xf = torch.empty(max(fine_max // 4, 1), device=dev)
+        self.ws = torch.empty(ws_max, dtype=torch.uint8, device=dev)
+        self.ws_bytes = ws_max
+        self.u = rnd(kd_max_elems * self.pool_mult)
+        self.delta = rnd(kd_max_elems * self.pool_mult, 0.5)
+        self.dout = rnd(kd_max_elems * self.pool_mult)
+        self.Bm = rnd(bc_max * self.pool_mult)
+        self.Cm = rnd(bc_max * self.pool_mult)
         self.cur_row = 0
         self.cur_bc = 0
         self.total_bytes = sum(scan_bytes(BATCH, kd, L)["total"] for kd, L in self.scans)
         self.bwd_bytes = sum(scan_bytes(BATCH, kd, L)["bwd"] for kd, L in self.scans)
 
-    def _slice(self, buf, cur, n):
-        if cur + n > buf.numel():
-            cur = 0
-        return buf[cur:cur + n], cur + n
+    def _bare_desc(self, kd, L):
+        d = self.Desc()
+        d.batch, d.dim, d.dstate, d.ngroups, d.seqlen = BATCH, kd, N_STATE, K_DIR, L
+        d.dtype, d.delta_softplus = 0, 1
+        p = lambda buf: ctypes.c_void_p(buf.data_ptr())  # noqa: E731
+        d.u, d.delta, d.B, d.C = p(self.u), p(self.delta), p(self.Bm), p(self.Cm)
+        for s in (d.u_stride, d.delta_stride, d.out_stride, d.dout_stride):
+            s[0], s[1] = kd * L, L
+        for s in (d.B_stride, d.C_stride):
+            s[0], s[1], s[2] = K_DIR * N_STATE * L, N_STATE * L, L
+        d.A_stride = N_STATE
+        return d
 
     def desc_for(self, kd, L):
         t = self.torch
@@ -268,9 +321,11 @@ class Workload:
             s[0], s[1], s[2] = K_DIR * N_STATE * L, N_STATE * L, L
         d.A_stride = N_STATE
         d.out, d.x = p(self.out), p(self.x)
-        d.workspace, d.workspace_bytes = p(self.ws), self.native.workspace_bytes(BATCH, kd)
+        d.workspace, d.workspace_bytes = p(self.ws), self.ws_bytes
         d.du, d.ddelta = p(self.du), p(self.dd)
         d.dA, d.dB, d.dC, d.dD, d.ddelta_bias = p(self.dA), p(self.dB), p(self.dC), p(self.dD), p(self.dbias)
+        if self.lib.nz_scan_fine_bytes(ctypes.byref(d)):  # this scan qualifies for the row-per-lane backward
+            d.xf = p(self.xf)
         _ = t
         return d, n_bc
 
@@ -281,7 +336,7 @@ class Workload:
         for kd, L in self.scans:
             d, n_bc = self.desc_for(kd, L)
             self.native.check(self.lib.nz_scan_fwd(ctypes.byref(d), sp), "nz_scan_fwd")
-            if (kd // K_DIR) > 16:  # several tiles share a dB/dC element -> accumulate into zeros
+            if not self.lib.nz_scan_bwd_overwrites_dbc(ctypes.byref(d)):  # several tiles share a dB/dC element
                 self.dB[:n_bc].zero_()
                 self.dC[:n_bc].zero_()
             if bwd_events is not None:
@@ -359,7 +414,139 @@ def e2e_run(dev, stream, steps, warmup):
     return dt, h2d, d2h
 
 
-def train_run(dev, world, steps, warmup, per_gpu_batch):
+def _median_ms(fn, stream, iters, warmup):
+    import torch
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def configs_run(dev, stream, peak):
+    """The other BASELINE configs, measured next to the configs[1] headline (parity-test shapes, not bench lines):
+    cfg0 = configs[0] (B=2, K=4, D=192, L=4096 fp32, split-view B/C) through the C ABI, fwd and fwd+bwd;
+    cfg2 = configs[2]'s 1-D scan (2, 64, 128^3) bf16 + z gate, fwd+bwd through selective_scan_fn;
+    cfg3 = configs[3]'s MambaND token counts (75 / 600): microseconds per selective_scan_fn call and launches."""
+    import torch
+
+    from nnuzoo_b200 import _native, selective_scan_fn
+    from nnuzoo_b200._native import NzScanDesc
+    lib = _native.lib()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    res = {}
+    # ---- cfg0 through the C ABI (kernel time: the Python wrapper would add more than the kernels take) ----
+    c = CFG0
+    kd, L, N, G, Bn = c["K"] * c["D"], c["L"], c["N"], c["K"], c["batch"]
+    u, delta, A, Bv, Cv, D, bias = cfg0_tensors(dev)
+    gout = torch.randn(Bn, kd, L, device=dev)
+    out, du, dd = torch.empty_like(u), torch.empty_like(u), torch.empty_like(u)
+    dB, dC = torch.zeros(Bn, G, N, L, device=dev), torch.zeros(Bn, G, N, L, device=dev)
+    dA, dD, db = torch.zeros(kd, N, device=dev), torch.zeros(kd, device=dev), torch.zeros(kd, device=dev)
+    x = torch.empty(Bn, kd, (L + _native.NZ_CHUNK - 1) // _native.NZ_CHUNK, N, device=dev)
+    d = NzScanDesc()
+    d.batch, d.dim, d.dstate, d.ngroups, d.seqlen, d.dtype, d.delta_softplus = Bn, kd, N, G, L, 0, 1
+    d.u, d.delta, d.A, d.B, d.C, d.D, d.delta_bias, d.dout = p(u), p(delta), p(A), p(Bv), p(Cv), p(D), p(bias), p(gout)
+    for st in (d.u_stride, d.delta_stride, d.out_stride, d.dout_stride):
+        st[0], st[1] = kd * L, L
+    for k in range(3):
+        d.B_stride[k], d.C_stride[k] = Bv.stride(k), Cv.stride(k)
+    d.A_stride = N
+    d.out, d.x, d.du, d.ddelta = p(out), p(x), p(du), p(dd)
+    d.dA, d.dB, d.dC, d.dD, d.ddelta_bias = p(dA), p(dB), p(dC), p(dD), p(db)
+    nfine = int(lib.nz_scan_fine_bytes(ctypes.byref(d)))
+    xf = torch.empty(max(nfine // 4, 1), device=dev)
+    if nfine:
+        d.xf = p(xf)
+    wsb = max(int(lib.nz_scan_workspace_bytes_bwd(ctypes.byref(d))), int(lib.nz_scan_workspace_bytes_cp(ctypes.byref(d))))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    d.workspace, d.workspace_bytes = p(ws), wsb
+    zero = not lib.nz_scan_bwd_overwrites_dbc(ctypes.byref(d))
+
+    def f_fwd():
+        _native.check(lib.nz_scan_fwd(ctypes.byref(d), sp), "nz_scan_fwd")
+
+    def f_both():
+        _native.check(lib.nz_scan_fwd(ctypes.byref(d), sp), "nz_scan_fwd")
+        if zero:
+            dB.zero_()
+            dC.zero_()
+        _native.check(lib.nz_scan_bwd(ctypes.byref(d), sp), "nz_scan_bwd")
+
+    by = scan_bytes(Bn, kd, L)
+    t_f, t_fb = _median_ms(f_fwd, stream, 100, 20), _median_ms(f_both, stream, 100, 20)
+    res["cfg0"] = {"shape": "B=2, K=4, D=192, N=16, L=4096, fp32, split-view B/C (BASELINE configs[0])",
+                   "fwd_us": t_f * 1e3, "fwd_gbps": by["fwd"] / t_f / 1e6, "fwd_frac": by["fwd"] / t_f / 1e6 / peak,
+                   "fwd_bwd_us": t_fb * 1e3, "fwd_bwd_gbps": by["total"] / t_fb / 1e6,
+                   "fwd_bwd_frac": by["total"] / t_fb / 1e6 / peak, "timing": "median of 100 after 20 warm-ups, CUDA events, C ABI",
+                   "note": "warm in L2 (214 MB of operands + results vs 126 MB L2); launch-latency bound"}
+    del u, delta, Bv, Cv, gout, out, du, dd, dB, dC, x, xf, ws
+    # ---- cfg2: the 1-D nets' scan ----
+    torch.manual_seed(3)
+    Bn, Dm, L = 2, 64, 128 ** 3
+    mk = lambda *sh: torch.randn(*sh, device=dev).to(torch.bfloat16)  # noqa: E731
+    leaves = [mk(Bn, Dm, L).requires_grad_(True), (0.5 * torch.randn(Bn, Dm, L, device=dev)).to(torch.bfloat16).requires_grad_(True),
+              mk(Bn, 1, 16, L).requires_grad_(True), mk(Bn, 1, 16, L).requires_grad_(True), mk(Bn, Dm, L).requires_grad_(True)]
+    A = (-torch.arange(1, 17, device=dev).float().repeat(Dm, 1)).requires_grad_(True)
+    Dp, bias = torch.ones(Dm, device=dev, requires_grad=True), torch.full((Dm,), -2.0, device=dev, requires_grad=True)
+    g2 = mk(Bn, Dm, L)
+
+    def f2_fwd():
+        with torch.no_grad():
+            selective_scan_fn(leaves[0], leaves[1], A, leaves[2], leaves[3], Dp, leaves[4], bias, True)
+
+    def f2():
+        o = selective_scan_fn(leaves[0], leaves[1], A, leaves[2], leaves[3], Dp, leaves[4], bias, True)
+        o.backward(g2)
+        for t in leaves + [A, Dp, bias]:
+            t.grad = None
+
+    E, S = Bn * Dm * L, Bn * 16 * L
+    t2f, t2 = _median_ms(f2_fwd, stream, 5, 2), _median_ms(f2, stream, 5, 2)
+    res["cfg2"] = {"shape": "u (2, 64, 2097152) bf16, z gate, one B/C group (BASELINE configs[2]'s 1-D scan)",
+                   "fwd_ms": t2f, "fwd_gbps": 2 * (4 * E + 2 * S) / t2f / 1e6,
+                   "fwd_bwd_ms": t2, "fwd_bwd_gbps": 2 * (11 * E + 6 * S) / t2 / 1e6,
+                   "fwd_bwd_frac": 2 * (11 * E + 6 * S) / t2 / 1e6 / peak,
+                   "timing": "median of 5 after 2 warm-ups through selective_scan_fn (autograd included)"}
+    del leaves, g2
+    torch.cuda.empty_cache()
+    # ---- cfg3: MambaND token counts ----
+    rows = []
+    for Dm, L in ((192, 600), (384, 600), (768, 75)):
+        lv = [torch.randn(2, Dm, L, device=dev, requires_grad=True), (0.5 * torch.randn(2, Dm, L, device=dev)).requires_grad_(True),
+              torch.randn(2, 1, 16, L, device=dev, requires_grad=True), torch.randn(2, 1, 16, L, device=dev, requires_grad=True),
+              torch.randn(2, Dm, L, device=dev, requires_grad=True)]
+        A = (-torch.arange(1, 17, device=dev).float().repeat(Dm, 1)).requires_grad_(True)
+        Dp, bias = torch.ones(Dm, device=dev, requires_grad=True), torch.full((Dm,), -2.0, device=dev, requires_grad=True)
+        g3 = torch.randn(2, Dm, L, device=dev)
+
+        def f3f():
+            with torch.no_grad():
+                selective_scan_fn(lv[0], lv[1], A, lv[2], lv[3], Dp, lv[4], bias, True)
+
+        def f3():
+            o = selective_scan_fn(lv[0], lv[1], A, lv[2], lv[3], Dp, lv[4], bias, True)
+            o.backward(g3)
+
+        n0 = _native.launch_count()
+        f3()
+        per_call = _native.launch_count() - n0
+        rows.append({"shape": [2, Dm, L], "fwd_us": _median_ms(f3f, stream, 50, 10) * 1e3,
+                     "fwd_bwd_us": _median_ms(f3, stream, 50, 10) * 1e3, "our_launches_fwd_bwd": per_call})
+    res["cfg3"] = {"what": "BASELINE configs[3] (MambaND2Net) token counts: microseconds per selective_scan_fn call "
+                           "(Python wrapper + allocations + launches), fp32, z gate", "calls": rows}
+    return res
+
+
+def train_run(dev, world, steps, warmup, per_gpu_batch, sync_bn=True, scaling="weak"):
     """The second half of BASELINE.json's metric: SS2D2Net (M2Net) training patches/s -- full optimisation steps
     (H2D of the pinned batch, bf16-autocast forward, Dice+CE deep-supervision loss, backward with the DDP gradient
     all-reduce over NCCL, clip, AdamW, loss read back) through nnuzoo_b200.train.Trainer.  Weak scaling: every rank
@@ -371,7 +558,7 @@ def train_run(dev, world, steps, warmup, per_gpu_batch):
     from nnuzoo_b200.train import Trainer, synthetic_batch
 
     torch.manual_seed(0)
-    trainer = Trainer(get_m2net(1, 4, True).train(), dev)
+    trainer = Trainer(get_m2net(1, 4, True).train(), dev, sync_bn=sync_bn)   # SyncBatchNorm as nnUNetTrainer.py:279-280
     data, targets = synthetic_batch(per_gpu_batch, 1, 4, seed=17 + dev.index)
     h2d = data.numel() * data.element_size() + sum(t.numel() * t.element_size() for t in targets)
     for _ in range(warmup):
@@ -383,14 +570,21 @@ def train_run(dev, world, steps, warmup, per_gpu_batch):
     n0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    loss = None
-    for _ in range(steps):
-        loss = float(trainer.train_step(data, targets).item())     # D2H read of the step's result
+    losses = torch.zeros(steps, device=dev)
+    for i in range(steps):
+        losses[i] = trainer.train_step(data, targets)             # the step's result stays on the device ...
+    loss = float(losses[-1].item())                                # ... and is read back once (no host sync per step)
     e1.record()
     torch.cuda.synchronize(dev)
     ms = max_over_ranks(e0.elapsed_time(e1) / steps, dev, world)
-    return {"patches_per_s": world * per_gpu_batch / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms,
-            "per_gpu_batch": per_gpu_batch, "global_batch": world * per_gpu_batch, "scaling": "weak",
+    if world > 1:
+        gb = torch.tensor([float(per_gpu_batch)], device=dev)
+        torch.distributed.all_reduce(gb)
+        global_batch = int(gb.item())
+    else:
+        global_batch = per_gpu_batch
+    return {"patches_per_s": global_batch / (ms * 1e-3), "unit": "patches/s", "ms_per_step": ms,
+            "per_gpu_batch": per_gpu_batch, "global_batch": global_batch, "scaling": scaling, "sync_bn": bool(sync_bn and world > 1),
             "steps": steps, "warmup": warmup, "autocast": "bf16", "loss": loss,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
             "our_kernel_launches_per_step": (_native.launch_count() - n0) // steps,
@@ -491,12 +685,23 @@ def run_gpu_arm(args):
                    "api": "nz_scan_fwd_bwd_host (include/nnuzoo_b200.h), pinned host buffers"}
         except Exception as ex:  # report, never fake
             e2e = {"value": None, "unit": "GB/s", "error": repr(ex)[:300]}
+    configs = None
+    if rank == 0 and not args.no_configs:
+        try:
+            configs = configs_run(dev, stream, peak)
+        except Exception as ex:  # report, never fake
+            configs = {"error": repr(ex)[:300]}
     train = None
     if not args.no_train:
-        del wl.u, wl.delta, wl.dout, wl.Bm, wl.Cm, wl.out, wl.du, wl.dd, wl.dB, wl.dC, wl.x
+        del wl.u, wl.delta, wl.dout, wl.Bm, wl.Cm, wl.out, wl.du, wl.dd, wl.dB, wl.dC, wl.x, wl.xf, wl.ws
         torch.cuda.empty_cache()
         try:
             train = train_run(dev, world, args.train_steps, 2, args.train_batch)
+            if world > 1:  # the reference's own split of a global batch of 12 (nnUNetTrainer.py:420-429): strong scaling
+                from nnuzoo_b200.train import split_global_batch
+                torch.cuda.empty_cache()
+                train["strong"] = train_run(dev, world, args.train_steps, 2, split_global_batch(BATCH, world)[rank],
+                                            scaling="strong (global batch 12 split as the reference does)")
         except Exception as ex:  # report, never fake
             train = {"patches_per_s": None, "error": repr(ex)[:300]}
     infer = None
@@ -518,13 +723,19 @@ def run_gpu_arm(args):
             "patches_per_s_scan_only": world * BATCH / (ms_per_step * 1e-3),
             "frac_of_hbm_peak": value / world / peak,
             "roofline": {"bound": "hbm", "achieved": bwd_gbps, "peak": peak, "unit": "GB/s", "frac": bwd_gbps / peak,
-                         "traffic": traffic_per_launch(), "peak_source": peak_src,
+                         "traffic": traffic_per_launch()[0], "traffic_git": traffic_per_launch()[1], "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": wl.bwd_bytes / len(wl.scans),
-                         "kernel": "nz::scan_bwd_kernel<float, M=8, LPR=16, WARPS=8, TMA> (persistent tiles of 16 rows x "
-                                   "128 steps; all 80 launches per step; algorithmic bytes 4*(5E+4S) per launch, "
-                                   "achieved = sum of bytes / sum of CUDA-event durations of those launches)",
-                         "share_of_step": bwd_ms / (ms_per_step * args.steps)},
-            "train": train, "infer": infer, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                         "kernel": "nz_scan_bwd: from 25 M elements the row-per-lane backward (nz::scan_rl_agg_kernel + "
+                                   "scan_rl_combine_kernel + nz::scan_bwd_rl_kernel, csrc/scan_rl_kernels.cuh), below that "
+                                   "nz::scan_bwd_kernel<float, 8, 16, 8, TMA>; all 80 calls per step; algorithmic bytes "
+                                   "4*(5E+4S) per call, achieved = sum of bytes / sum of CUDA-event durations of the calls",
+                         "share_of_step": bwd_ms / (ms_per_step * args.steps),
+                         "mufu_floor_frac": 0.54,
+                         "mufu_floor_note": "16 ex2 per element and pass at 16 lanes/clk/SM: the row-per-lane backward "
+                                            "evaluates them twice (aggregate pass + main pass, 2.3 clk/elt) against an HBM "
+                                            "floor of 1.24 clk/elt at the stage-1 shape, so MUFU caps it at 0.54 of the "
+                                            "measured HBM peak (the single-pass warp-scan kernel at 0.90)"},
+            "configs": configs, "train": train, "infer": infer, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:
@@ -542,9 +753,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-infer", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0] / [2] / [3] side measurements")
     ap.add_argument("--infer-slices", type=int, default=200)
-    ap.add_argument("--infer-tile-batch", type=int, default=4)
-    ap.add_argument("--train-steps", type=int, default=3)
+    ap.add_argument("--infer-tile-batch", type=int, default=5)
+    ap.add_argument("--train-steps", type=int, default=10)
     ap.add_argument("--train-batch", type=int, default=BATCH, help="per-GPU batch of the M2Net training leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -116,9 +116,10 @@ typedef struct NzScanDesc {
 
   /* ---- fine checkpoints (ABI v3; optional) ---- */
   float* xf;                /* NULL, or nz_scan_fine_bytes() bytes: (batch, dim, L / NZ_FINE, N) fp32, h at the end of
-                               every NZ_FINE-step block.  Written by nz_scan_fwd when non-NULL; nz_scan_bwd given the
-                               same buffer (and a workspace of nz_scan_workspace_bytes_bwd() bytes) runs the row-per-lane
-                               backward, otherwise the warp-scan backward that only needs x. */
+                               every NZ_FINE-step block.  Written by nz_scan_fwd when non-NULL and the problem
+                               qualifies (nz_scan_fine_bytes() > 0; ignored otherwise); nz_scan_bwd given the same buffer
+                               (and a workspace of nz_scan_workspace_bytes_bwd() bytes) runs the row-per-lane backward,
+                               otherwise the warp-scan backward that only needs x. */
 } NzScanDesc;
 
 /* Bytes of scratch a call with this batch / dim needs (same for forward and backward). */

@@ -60,7 +60,6 @@ class NzConv1dDesc(ctypes.Structure):
 
 _lib = None
 _lock = threading.Lock()
-_bound_device = {}
 
 
 class NativeLibraryError(RuntimeError):
@@ -152,10 +151,9 @@ def check(rc: int, what: str) -> None:
 
 def bind_device(index: int) -> None:
     """Make `index` current in the library's own CUDA runtime for the calling thread."""
-    tid = threading.get_ident()
-    if _bound_device.get(tid) != index:
-        check(lib().nz_set_device(int(index)), "nz_set_device")
-        _bound_device[tid] = index
+    # unconditional: another library (PyTorch included) may have switched the thread's current device since the last
+    # call, and the call is cheap
+    check(lib().nz_set_device(int(index)), "nz_set_device")
 
 
 def workspace_bytes(batch: int, dim: int) -> int:

@@ -527,8 +527,9 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   const bool tma = setup_tma(d, a, bwd);
   const bool has_z = d->z != nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (d->xf && !rl_shape_ok(d))
-    return fail(NZ_EINVAL, "xf given but the row-per-lane backward does not apply to this problem (nz_scan_fine_bytes() == 0)");
+  // (an xf the problem does not qualify for -- nz_scan_fine_bytes() == 0 -- is ignored: the forward does not write it and
+  // the backward takes the warp-scan kernels, which only need x)
+  const bool use_xf = d->xf && rl_shape_ok(d);
   if (!bwd && rl_fwd_usable(d)) {
     cudaError_t e = d->dtype == NZ_F32    ? run_fwd_rl<float>(d, st)
                     : d->dtype == NZ_BF16 ? run_fwd_rl<__nv_bfloat16>(d, st)
@@ -536,7 +537,7 @@ static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
     if (e != cudaSuccess) return fail(NZ_ECUDA, "scan_fwd (row-per-lane) launch failed: %s", cudaGetErrorString(e));
     return NZ_OK;
   }
-  if (!bwd && d->xf) {
+  if (!bwd && use_xf) {
     if (!tma) return fail(NZ_EINVAL, "xf given but the forward cannot take the TMA path for this problem");
     a.xf = d->xf;
   }

@@ -162,13 +162,17 @@ __device__ __forceinline__ unsigned smid() {
 }
 
 // ---- chained hand-off slots ----
+// {value, tag} travel as ONE 64-bit scalar access: the PTX memory model guarantees single-copy atomicity for an aligned
+// b64 access, not for a v2.b32 vector access (which it treats as two scalar accesses in unspecified order).
 __device__ __forceinline__ void slot_store(unsigned long long* p, float v, unsigned tag) {
-  asm volatile("st.relaxed.gpu.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag) : "memory");
+  const unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 __device__ __forceinline__ void slot_load(const unsigned long long* p, float& v, unsigned& tag) {
-  unsigned bits;
-  asm volatile("ld.relaxed.gpu.global.v2.b32 {%0, %1}, [%2];" : "=r"(bits), "=r"(tag) : "l"(p) : "memory");
-  v = __uint_as_float(bits);
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  v = __uint_as_float((unsigned)(w & 0xffffffffull));
+  tag = (unsigned)(w >> 32);
 }
 
 // Poll a hand-off slot until it carries `expect`.  (Backing off with nanosleep when the slot's current tag shows

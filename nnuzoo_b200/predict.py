@@ -12,10 +12,11 @@ What is different, by design:
   * ``tile_batch`` tiles go through the network per forward (the reference uses batch 1, :614), and the mirrored
     copies of a batch are stacked into the same forward when ``stack_mirrors`` -- an eval-mode network treats samples
     independently, so the per-tile results are the same numbers;
-  * the tile list is sharded ``slicers[rank::world]`` over the ranks of the default process group; every rank
-    accumulates its own tiles and the two accumulators are summed with ONE all-reduce each (NCCL over NVLink)
-    *before* the division -- exact for disjoint tiles (2-D slices of a volume), fp16 summation-order tolerance
-    for overlapping ones.
+  * the tile list is sharded over the ranks of the default process group.  Disjoint tiles (2-D slices of a volume,
+    one tile per slice -- config 5): contiguous balanced runs of slices per rank, merged with ONE all-gather of the
+    finished slabs (exact).  Overlapping tiles: ``slicers[rank::world]``, every rank accumulates its own tiles and
+    the two accumulators are summed with one all-reduce each (NCCL over NVLink) *before* the division (fp16
+    summation-order tolerance).
 """
 from __future__ import annotations
 
@@ -161,7 +162,18 @@ class SlidingWindowPredictor:
         data, revert = pad_to_patch(image, self.patch_size)
         data = data.to(dev)
         slicers = sliding_window_slicers(data.shape[1:], self.patch_size, self.tile_step_size)
-        mine = slicers[rank::world]
+        # Sharding.  2-D tiles of a volume whose slices are covered by ONE tile each are disjoint in the output: every
+        # rank then takes a contiguous, balanced run of slices (200 slices on 8 ranks = 25 each; `rank::world` with
+        # tile batches of 4 gave 7, 7, 6, ... forwards) and the merge is an all-gather of the finished slabs -- 1/world
+        # of the bytes of the all-reduce below and no summation at all.  Everything else (overlapping tiles) keeps
+        # `rank::world` and the all-reduce(sum) of both accumulators before the division.
+        disjoint = (ddp and len(self.patch_size) == data.dim() - 2 and len(slicers) == data.shape[1])
+        if disjoint:
+            per = -(-len(slicers) // world)
+            z0, z1 = min(rank * per, len(slicers)), min((rank + 1) * per, len(slicers))
+            mine = slicers[z0:z1]
+        else:
+            mine = slicers[rank::world]
         logits = torch.zeros((self.num_heads, *data.shape[1:]), dtype=self.results_dtype, device=dev)
         n_pred = torch.zeros(data.shape[1:], dtype=self.results_dtype, device=dev)
         gaussian = (compute_gaussian(self.patch_size, 1.0 / 8, 10, self.results_dtype, dev) if self.use_gaussian
@@ -176,10 +188,18 @@ class SlidingWindowPredictor:
                 for sl, p in zip(group, pred):
                     logits[sl] += p
                     n_pred[sl[1:]] += gaussian
-        if ddp:  # the one exchange step of this path: sum the per-rank accumulators, then divide
-            dist.all_reduce(logits, op=dist.ReduceOp.SUM)
-            dist.all_reduce(n_pred, op=dist.ReduceOp.SUM)
-        logits /= n_pred
+        if disjoint:  # the one exchange step of this path: gather every rank's finished run of slices
+            logits[:, z0:z1] /= n_pred[z0:z1]
+            slab = torch.zeros((self.num_heads, per, *data.shape[2:]), dtype=self.results_dtype, device=dev)
+            slab[:, :z1 - z0] = logits[:, z0:z1]
+            parts = [torch.empty_like(slab) for _ in range(world)]
+            dist.all_gather(parts, slab)
+            logits = torch.cat(parts, 1)[:, :data.shape[1]]
+        else:
+            if ddp:  # overlapping tiles: sum the per-rank accumulators, then divide
+                dist.all_reduce(logits, op=dist.ReduceOp.SUM)
+                dist.all_reduce(n_pred, op=dist.ReduceOp.SUM)
+            logits /= n_pred
         if bool(torch.isinf(logits).any()):
             raise RuntimeError("Encountered inf in predicted array: reduce value_scaling_factor or use fp32 results")
         return logits[(slice(None), *revert[1:])]

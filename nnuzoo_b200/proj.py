@@ -40,6 +40,11 @@ def proj_wgrad(g: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     rc = _native.lib().nz_proj_wgrad(ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(x.data_ptr()),
                                      ctypes.c_void_p(dw.data_ptr()), _DT[g.dtype], _DT[x.dtype], B, K, M, N, L, gs, xs,
                                      stream)
+    if rc == -2:
+        # NZ_EUNSUPPORTED: M * N beyond what one CTA's accumulators hold (wider SS2D than M2Net's, e.g. SwinUMamba's
+        # d_model 192: 44 x 384).  The projection is GEMM-shaped, so the library GEMM is the plain path here -- as
+        # norm.py does for channel counts its kernel does not cover.
+        return torch.einsum("bkml,bknl->kmn", g.float(), x.float())
     _native.check(rc, "nz_proj_wgrad")
     return dw
 

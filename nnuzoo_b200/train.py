@@ -82,9 +82,10 @@ class DiceCELoss(nn.Module):
         sum_pred = prob.sum(axes)
         if self.batch_dice:
             if self.ddp:
-                intersect = _AllGatherWithGrad.apply(intersect).sum(0)
-                sum_pred = _AllGatherWithGrad.apply(sum_pred).sum(0)
-                sum_gt = _AllGatherWithGrad.apply(sum_gt.to(sum_pred.dtype)).sum(0)
+                # the reference gathers the three statistics one by one (dice.py:107-111); stacked they are one
+                # all-gather (and one all-reduce in the backward) per head instead of three
+                packed = torch.stack((intersect, sum_pred, sum_gt.to(sum_pred.dtype)), 0)
+                intersect, sum_pred, sum_gt = _AllGatherWithGrad.apply(packed).sum(0).unbind(0)
             intersect, sum_pred, sum_gt = intersect.sum(0), sum_pred.sum(0), sum_gt.sum(0)
         dc = (2 * intersect + self.smooth) / torch.clip(sum_gt + sum_pred + self.smooth, 1e-8)
         return ce - dc.mean()
@@ -135,6 +136,9 @@ class Trainer:
         self.optimizer = torch.optim.AdamW(self.module.parameters(), lr=lr, weight_decay=weight_decay, eps=1e-5,
                                            betas=(0.9, 0.999))
         self.autocast_dtype, self.clip = autocast_dtype, clip
+        # fp16 autocast needs the reference's loss scaling (nnUNetTrainer.py:1128-1139); bf16 does not
+        self.scaler = (torch.amp.GradScaler(self.device.type) if autocast_dtype == torch.float16 and
+                       self.device.type == "cuda" else None)
 
     def train_step(self, data: torch.Tensor, target) -> torch.Tensor:
         """``data`` / ``target`` may be (pinned) host tensors; returns the detached loss on the device."""
@@ -148,7 +152,14 @@ class Trainer:
         with torch.autocast(dev.type, dtype=self.autocast_dtype, enabled=dev.type == "cuda"):
             out = self.network(data)
             loss = self.loss(out, target)
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(self.module.parameters(), self.clip)
-        self.optimizer.step()
+        if self.scaler is not None:  # scale -> unscale_ -> clip -> step -> update, as the reference does
+            self.scaler.scale(loss).backward()
+            self.scaler.unscale_(self.optimizer)
+            torch.nn.utils.clip_grad_norm_(self.module.parameters(), self.clip)
+            self.scaler.step(self.optimizer)
+            self.scaler.update()
+        else:
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(self.module.parameters(), self.clip)
+            self.optimizer.step()
         return loss.detach()

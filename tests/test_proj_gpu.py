@@ -72,3 +72,16 @@ def test_cpu_tensors_are_refused():
     from nnuzoo_b200.proj import proj_wgrad
     with pytest.raises(RuntimeError):
         proj_wgrad(torch.zeros(1, 1, 2, 4), torch.zeros(1, 1, 2, 4))
+
+
+def test_wide_projection_falls_back_to_the_library_gemm():
+    """M * N above the kernel's accumulator budget (d_model 192: (R + 2N) x d_inner = 44 x 384) must not raise."""
+    from nnuzoo_b200.proj import grouped_proj
+    torch.manual_seed(0)
+    x = torch.randn(2, 4, 384, 96, device="cuda", requires_grad=True)
+    w = torch.randn(4, 44, 384, device="cuda", requires_grad=True)
+    y = grouped_proj(x, w)
+    g = torch.randn_like(y)
+    y.backward(g)
+    ref = torch.einsum("bkml,bknl->kmn", g.double(), x.detach().double())
+    assert float((w.grad.double() - ref).abs().max() / ref.abs().max()) < 1e-4

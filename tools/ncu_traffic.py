@@ -44,16 +44,35 @@ def main(path, out=None):
     print(f"{len(per)} launches, {tot / 1e3:.2f} ms summed (serialised, cold cache)")
     for k, v in by.most_common():
         print(f"  {k:40s} launches {cnt[k]:4d}  time {v / 1e3:9.3f} ms  share {v / tot:6.1%}")
-    bwd = [d for d in per.values() if "scan_bwd" in d["kernel"]]
+    # every launch an nz_scan_bwd call makes: the warp-scan kernel, or the row-per-lane trio (backward aggregate pass =
+    # scan_rl_agg_kernel<T, z, false>, its combine, main pass)
+    order = list(per.values())
+    bwd = []
+    for i, d in enumerate(order):
+        k = d["kernel"]
+        kk = k.replace(" ", "")
+        # last template argument of the aggregate kernel: kFwd
+        is_bwd_agg = "scan_rl_agg_kernel" in kk and any(t in kk for t in ("(bool)0>(", "false>(", ",0>("))
+        is_bwd_comb = "combine" in k and i > 0 and order[i - 1] in bwd and "agg" in order[i - 1]["kernel"]
+        if "scan_bwd" in k or is_bwd_agg or is_bwd_comb:
+            bwd.append(d)
     if bwd and "dram__bytes_read.sum" in bwd[0]:
-        traffic = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in bwd) / len(bwd)
         scans = bench.m2net_scan_list(512)
-        algo = sum(bench.scan_bytes(bench.BATCH, kd, L)["bwd"] for kd, L in scans) / len(scans)
-        print(f"scan_bwd: {len(bwd)} launches, DRAM traffic {traffic / 1e6:.1f} MB per launch vs algorithmic "
-              f"{algo / 1e6:.1f} MB per launch (x{traffic / algo:.3f})")
+        calls = len(scans)
+        traffic = sum(d["dram__bytes_read.sum"] + d["dram__bytes_write.sum"] for d in bwd) / calls
+        algo = sum(bench.scan_bytes(bench.BATCH, kd, L)["bwd"] for kd, L in scans) / calls
+        t_bwd = sum(d.get("gpu__time_duration.sum", 0.0) for d in bwd)
+        print(f"nz_scan_bwd: {len(bwd)} launches in {calls} calls, {t_bwd / 1e3:.2f} ms ({t_bwd / tot:.1%} of the step), DRAM "
+              f"traffic {traffic / 1e6:.1f} MB per call vs algorithmic {algo / 1e6:.1f} MB per call (x{traffic / algo:.3f})")
         if out:
+            import subprocess
+            try:
+                rev = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+            except Exception:
+                rev = None
             json.dump({"dram_bytes_per_launch": traffic, "algorithmic_bytes_per_launch": algo, "launches": len(bwd),
-                       "ratio": traffic / algo, "source": os.path.basename(path),
+                       "calls": calls, "ratio": traffic / algo, "share_of_step_ncu": t_bwd / tot, "git": rev,
+                       "source": os.path.basename(path), "unit": "per nz_scan_bwd call (1 or 3 launches)",
                        "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                               "--clock-control none, bench.py --steps 1 (NZ_BENCH_PROFILE=1)"}, open(out, "w"), indent=1)
 
