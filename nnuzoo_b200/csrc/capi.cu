@@ -432,6 +432,8 @@ static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
   rl_plan(d, &r.nchunks, &r.tpc);
   r.softplus = d->delta_softplus;
   r.single = r.nrb == 1;
+  r.v2 = 1;
+  if (const char* e = getenv("NZ_RL_BWD2")) r.v2 = atoi(e) != 0;  // A/B against the slab version
   if (r.nchunks > 1) {
     const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
     char* base = reinterpret_cast<char*>(d->workspace) + nz_scan_workspace_bytes(d);

@@ -14,6 +14,9 @@ static cudaError_t launch_rl_one(const RlArgs& a, cudaStream_t st) {
   auto maink0 = scan_bwd_rl_kernel<T, kHasZ, false>;  // several warps per group: RED
   constexpr size_t agg_smem = 1024 + 2 * ((kHasZ ? 3 : 2) * RlCfg<T>::ROWT + RlCfg<T>::BCT) + 64;
   constexpr size_t main_smem = RlMainSmem<T, kHasZ>::bytes();
+  auto main2k1 = scan_bwd_rl2_kernel<T, kHasZ, true>;
+  auto main2k0 = scan_bwd_rl2_kernel<T, kHasZ, false>;
+  constexpr size_t main2_smem = RlMain2Smem<T, kHasZ>::bytes();
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(agg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -21,6 +24,10 @@ static cudaError_t launch_rl_one(const RlArgs& a, cudaStream_t st) {
       e = cudaFuncSetAttribute(maink0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(maink1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(main2k0, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(main2k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -31,7 +38,12 @@ static cudaError_t launch_rl_one(const RlArgs& a, cudaStream_t st) {
     scan_rl_combine_kernel<<<(unsigned)((nrows * kMaxState + 127) / 128), 128, 0, st>>>(a.aggG, a.aggQ, a.Rin, nrows,
                                                                                       a.nchunks, 0);
   }
-  if (a.single)
+  if (a.v2) {
+    if (a.single)
+      main2k1<<<(unsigned)(rbt * a.nchunks), 32, main2_smem, st>>>(a);
+    else
+      main2k0<<<(unsigned)(rbt * a.nchunks), 32, main2_smem, st>>>(a);
+  } else if (a.single)
     maink1<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
   else
     maink0<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);

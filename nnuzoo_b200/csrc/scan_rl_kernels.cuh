@@ -60,6 +60,7 @@ struct alignas(64) RlArgs {
   int softplus;
   int single;    // one warp owns each dB / dC element (dpg == 32): plain stores instead of RED
   unsigned zero; // always 0 (see order_after)
+  int v2;        // backward main pass: 1 = butterfly version (scan_bwd_rl2_kernel), 0 = slab version
 };
 
 // ---- exp2 on the FMA pipe ----
@@ -632,6 +633,327 @@ __global__ void __launch_bounds__(32, NZ_RL_BWD_MINB) scan_bwd_rl_kernel(const _
   // (dim)-shaped sums: over batch and chunks with fp32 atomics
 #pragma unroll
   for (int n = 0; n < kMaxState; ++n) atomicAdd(a.dA + (long)d * kMaxState + n, dAacc[n]);
+  if (a.dD) atomicAdd(a.dD + d, dD_acc);
+  if (a.dbias) atomicAdd(a.dbias + d, db_acc);
+}
+
+// ================================================================================================
+// Main pass, butterfly version: the dB / dC row reduction stays in registers
+// ================================================================================================
+// The slab version above moves every dB / dC product through shared memory (256 bytes per element: its shared-memory
+// floor of 2.7 clk/element is the largest pipe cost of the pass, and the STS -> LDS -> add -> SHFL chain needs the
+// hand-made scheduling fences).  Here the 32 rows of the warp are summed by butterfly exchanges:
+//   * lane l evaluates state n = s ^ (l & 3) in code slot s (A2 / R / dA / h_in are loaded with the permuted index, the
+//     B / C broadcasts become 4 adjacent 32-byte rows = still one wavefront).  Lanes l and l ^ 1 then hold the SAME state
+//     in slots s and s ^ 1, so "keep the even slot, send the odd slot" sums lane pairs without a single select; the
+//     same holds for l ^ 2 and slots s, s ^ 2.  A quad of slots (64 products per lane) therefore collapses to 16 values
+//     per lane, each the sum over 4 lanes, with 48 SHFL + 24 FADD2;
+//   * the remaining three lane bits split those 16 values (array B / C, time half, time pair) with selects:
+//     14 SHFL + 28 SEL + 7 FADD2, after which a lane owns one (array, state, time pair) of the quad = one 8-byte store.
+// 248 shuffle wavefronts per block of 8 steps against ~640 for the slab, no __syncwarp in the state loop.
+template <typename T, bool kHasZ>
+struct RlMain2Smem {
+  static constexpr int NROWT = kHasZ ? 4 : 3;
+  static constexpr int RB = 32 * kFine * (int)sizeof(T);
+  static constexpr int XB = 32 * kMaxState * 4;
+  static constexpr int RSTAGE = ((NROWT * RB + 1023) / 1024) * 1024 + XB;
+  static constexpr int OFF_XF = RSTAGE - XB;
+  static constexpr int BB = kMaxState * kFine * (int)sizeof(T);
+  static constexpr int BSTAGE = 2 * BB;
+  static constexpr int OFF_BC = 2 * RSTAGE;
+  static constexpr int OFF_BARS = OFF_BC + 2 * BSTAGE;
+  static constexpr int TOTAL = OFF_BARS + 64;
+  static constexpr size_t bytes() { return 1024 + TOTAL; }
+};
+
+#ifndef NZ_RL_BWD2_MINB
+#define NZ_RL_BWD2_MINB 12
+#endif
+
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int mask) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+}
+__device__ __forceinline__ float2 sel2(bool p, float2 a, float2 b) { return make_float2(p ? a.x : b.x, p ? a.y : b.y); }
+
+// state (4q + jj)'s 8 steps of a per-block B / C tile, jj = the lane's permuted low bits already folded into `base`
+template <typename T>
+__device__ __forceinline__ void lds_bc2(uint32_t base, int q, float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    const uint32_t o = (uint32_t)q * 128u, sw = (uint32_t)(q & 1) << 4;
+    unpack16<T>(lds128(base + o + sw), &v[0]);
+    unpack16<T>(lds128(base + o + (sw ^ 16u)), &v[4]);
+  } else {
+    unpack16<T>(lds128(base + (uint32_t)q * 64u), &v[0]);
+  }
+}
+
+template <typename T, bool kHasZ, bool kSingle>
+__global__ void __launch_bounds__(32, NZ_RL_BWD2_MINB) scan_bwd_rl2_kernel(const __grid_constant__ RlArgs a) {
+  using Cfg = RlCfg<T>;
+  using SM = RlMain2Smem<T, kHasZ>;
+  constexpr int NBLK = Cfg::NBLK, RB = SM::RB, BB = SM::BB;
+  constexpr int ROWS_TX = SM::NROWT * RB + SM::XB;
+  constexpr uint32_t RP = kFine * sizeof(T);  // pitch of a state row in a B / C tile
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BARS);  // [0],[1] row stages, [2],[3] B/C stages
+  const uint32_t smem_s = keep(smem_u32(smem));
+  const uint32_t bc_s = smem_s + SM::OFF_BC;
+  const int lane = threadIdx.x;
+  const int m = lane & 3;  // this lane's state permutation: slot s holds state s ^ m
+
+  const int item = blockIdx.x;
+  const int c = item % a.nchunks;
+  int w = item / a.nchunks;
+  const int rb = w % a.nrb;
+  w /= a.nrb;
+  const int g = w % a.ngroups, b = w / a.ngroups;
+  const int d0 = g * a.dpg + rb * 32, d = d0 + lane;
+  const long rowg = (long)b * a.dim + d;
+  const int t_lo = c * a.tpc, t_hi = min(a.ntl, t_lo + a.tpc);
+  const int j_lo = t_lo * NBLK, j_hi = t_hi * NBLK;  // fine blocks [j_lo, j_hi), walked last to first
+
+  auto issue_rows = [&](int j, int s) {
+    uint8_t* st = smem + s * SM::RSTAGE;
+    mbar_arrive_expect_tx(&bars[s], ROWS_TX);
+    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, d0, b);
+    tma_load_4d(st + RB, &a.tm_delta, &bars[s], 0, j, d0, b);
+    tma_load_4d(st + 2 * RB, &a.tm_dout, &bars[s], 0, j, d0, b);
+    if (kHasZ) tma_load_4d(st + 3 * RB, &a.tm_z, &bars[s], 0, j, d0, b);
+    tma_load_4d(st + SM::OFF_XF, &a.tm_xf, &bars[s], 0, j - 1, d0, b);  // block -1 is out of bounds: zero fill
+  };
+  auto issue_bc = [&](int j, int s) {
+    uint8_t* st = smem + SM::OFF_BC + s * SM::BSTAGE;
+    mbar_arrive_expect_tx(&bars[2 + s], SM::BSTAGE);
+    tma_load_5d(st, &a.tm_B, &bars[2 + s], 0, j, 0, g, b);
+    tma_load_5d(st + BB, &a.tm_C, &bars[2 + s], 0, j, 0, g, b);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    issue_rows(j_hi - 1, 0);
+    issue_bc(j_hi - 1, 0);
+    if (j_hi - 2 >= j_lo) {
+      issue_rows(j_hi - 2, 1);
+      issue_bc(j_hi - 2, 1);
+    }
+  }
+  __syncwarp();
+  float A2[kMaxState], R[kMaxState], dAacc[kMaxState];
+  {
+    const float* rin = a.Rin + (rowg * a.nchunks + c) * kMaxState;
+    const float* Ar = a.A + (long)d * a.A_ds;
+#pragma unroll
+    for (int s = 0; s < kMaxState; ++s) {
+      A2[s] = __ldg(Ar + (s ^ m)) * kLog2e;
+      R[s] = a.nchunks > 1 ? __ldg(rin + (s ^ m)) : 0.f;  // a_{t+1} dh_{t+1} entering the chunk's last step
+      dAacc[s] = 0.f;
+    }
+  }
+  const float Dv = a.D ? __ldg(a.D + d) : 0.f;
+  const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
+  float dD_acc = 0.f, db_acc = 0.f;
+
+  // B / C rows of the lane's four permuted low state bits, relative to a tile
+  uint32_t bco[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) bco[j] = keep((uint32_t)(j ^ m) * RP);
+  // h entering the block: lane's 64 bytes of the xf tile, 16-byte pieces swizzled with (row >> 1) & 3 (SWIZZLE_64B)
+  const uint32_t xf_l = keep((uint32_t)SM::OFF_XF + (uint32_t)lane * 64u);
+  const uint32_t xf_key = (uint32_t)((lane >> 1) & 3);
+  const bool m0 = (lane & 1) != 0, m1 = (lane & 2) != 0;
+  const bool p2 = (lane & 4) != 0, p3 = (lane & 8) != 0, p4 = (lane & 16) != 0;
+  // where this lane's share of the reduced dB / dC goes: array p2, state 4q + m, steps 4 p3 + 2 p4 (+1) of the block
+  char* dG0 = reinterpret_cast<char*>((p2 ? a.dC : a.dB) + (((long)b * a.ngroups + g) * kMaxState + m) * a.L +
+                                      (p3 ? 4 : 0) + (p4 ? 2 : 0));
+  long Lq = a.L * 16;  // byte pitch of four state rows of dB / dC
+  asm volatile("" : "+l"(Lq));
+
+  int k = 0;
+#pragma unroll 1
+  for (int jb = j_hi - 1; jb >= j_lo; --jb, ++k) {
+    const int s = k & 1;
+    const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+    mbar_wait(&bars[s], ph);
+    const uint32_t rst = smem_s + s * SM::RSTAGE;
+    float dl[8], dlu[8], dy[8], uu[8], sB[8], ddl[8];
+    float yv[kHasZ ? 8 : 1], dzf[kHasZ ? 8 : 1];
+    lds_blockrow<T>(rst, lane, uu);
+    lds_blockrow<T>(rst + RB, lane, dl);
+    lds_blockrow<T>(rst + 2 * RB, lane, dy);
+    if constexpr (kHasZ) {
+      float zz[8];
+      lds_blockrow<T>(rst + 3 * RB, lane, zz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float sg = sigmoid_f(zz[i]);
+        dzf[i] = dy[i] * sg * (1.f + zz[i] * (1.f - sg));  // dout * d silu(z)/dz
+        dy[i] = dy[i] * zz[i] * sg;                         // dout * silu(z)
+        yv[i] = Dv * uu[i];
+      }
+    }
+    float hp[kMaxState];  // h entering the block, in slot order
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = lds128(rst + xf_l + (((uint32_t)q ^ xf_key) << 4));
+      const float x = __uint_as_float(v.x), y = __uint_as_float(v.y), z = __uint_as_float(v.z), ww = __uint_as_float(v.w);
+      const float x1 = m0 ? y : x, y1 = m0 ? x : y, z1 = m0 ? ww : z, w1 = m0 ? z : ww;
+      hp[4 * q + 0] = m1 ? z1 : x1;
+      hp[4 * q + 1] = m1 ? w1 : y1;
+      hp[4 * q + 2] = m1 ? x1 : z1;
+      hp[4 * q + 3] = m1 ? y1 : w1;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = dl[i] + bias;
+      if (a.softplus) x = softplus_f(x);
+      dl[i] = x;
+      dlu[i] = x * uu[i];
+      sB[i] = 0.f;
+      ddl[i] = 0.f;
+    }
+    // this stage's row data now lives in registers: request the block after the next one into it
+    __syncwarp();
+    if (lane == 0 && jb - 2 >= j_lo) issue_rows(jb - 2, s);
+    mbar_wait(&bars[2 + s], ph);
+    const uint32_t tB = bc_s + s * SM::BSTAGE;
+    uint32_t tbj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) tbj[j] = tB + bco[j];
+    char* dGq = dG0 + (long)jb * (kFine * 4);
+
+    float bcv[2][2][8];  // [buffer][B, C][step]: the next slot's rows are requested before the current slot's math
+    lds_bc2<T>(tbj[0], 0, bcv[0][0]);
+    lds_bc2<T>(tbj[0] + BB, 0, bcv[0][1]);
+    float2 K0[8], K1[8];  // [0..3] dB, [4..7] dC of a slot pair, as time pairs
+#pragma unroll
+    for (int n = 0; n < kMaxState; ++n) {  // n = code slot; the state is n ^ m
+      float (&bv)[8] = bcv[n & 1][0];
+      float (&cdy)[8] = bcv[n & 1][1];
+      if (n + 1 < kMaxState) {
+        lds_bc2<T>(tbj[(n + 1) & 3], (n + 1) >> 2, bcv[(n + 1) & 1][0]);
+        lds_bc2<T>(tbj[(n + 1) & 3] + BB, (n + 1) >> 2, bcv[(n + 1) & 1][1]);
+      }
+      const float An = A2[n] * kLn2;
+      float av[8], hh[8], dd[8];
+      [[maybe_unused]] float cz[kHasZ ? 8 : 1];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 x2 = mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n]));
+        av[2 * kk] = ex2_approx(x2.x);
+        av[2 * kk + 1] = ex2_approx(x2.y);
+        const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
+        hh[2 * kk] = b2.x;  // b_t until the recurrence overwrites it with h_t
+        hh[2 * kk + 1] = b2.y;
+        if constexpr (kHasZ) {
+          cz[2 * kk] = cdy[2 * kk];
+          cz[2 * kk + 1] = cdy[2 * kk + 1];
+        }
+        const float2 c2 = mul2(f2(cdy[2 * kk], cdy[2 * kk + 1]), f2(dy[2 * kk], dy[2 * kk + 1]));
+        cdy[2 * kk] = c2.x;
+        cdy[2 * kk + 1] = c2.y;
+      }
+      // forward recurrence for h, reverse recurrence for dh (independent chains)
+      float bsave[8];
+      float h = hp[n];
+      float dh = cdy[7] + R[n];
+      dd[7] = dh;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        bsave[i] = hh[i];
+        h = fmaf(av[i], h, hh[i]);
+        hh[i] = h;
+        if (i < 7) {
+          const int j = 6 - i;
+          dh = fmaf(av[j + 1], dh, cdy[j]);
+          dd[j] = dh;
+        }
+      }
+      R[n] = av[0] * dd[0];  // R leaving the block
+      // element-wise products, packed over time pairs
+      float2 gs2 = f2(0.f, 0.f);
+      float2 V[8];  // this slot's dB (0..3) and dC (4..7) products
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 h2 = f2(hh[2 * kk], hh[2 * kk + 1]);
+        const float2 d2 = f2(dd[2 * kk], dd[2 * kk + 1]);
+        V[4 + kk] = mul2(f2(dy[2 * kk], dy[2 * kk + 1]), h2);  // dC_t[n] of this row
+        const float2 ah2 = sub2(h2, f2(bsave[2 * kk], bsave[2 * kk + 1]));  // a_t h_{t-1}
+        const float2 gq2 = mul2(d2, ah2);
+        float2 ddl2 = f2(ddl[2 * kk], ddl[2 * kk + 1]);
+        ddl2 = fma2(f2(An, An), gq2, ddl2);
+        ddl[2 * kk] = ddl2.x;
+        ddl[2 * kk + 1] = ddl2.y;
+        gs2 = fma2(f2(dl[2 * kk], dl[2 * kk + 1]), gq2, gs2);
+        V[kk] = mul2(d2, f2(dlu[2 * kk], dlu[2 * kk + 1]));  // dB_t[n] of this row
+        float2 s2 = f2(sB[2 * kk], sB[2 * kk + 1]);
+        s2 = fma2(d2, f2(bv[2 * kk], bv[2 * kk + 1]), s2);
+        sB[2 * kk] = s2.x;
+        sB[2 * kk + 1] = s2.y;
+        if constexpr (kHasZ) {
+          float2 y2 = f2(yv[2 * kk], yv[2 * kk + 1]);
+          y2 = fma2(f2(cz[2 * kk], cz[2 * kk + 1]), h2, y2);
+          yv[2 * kk] = y2.x;
+          yv[2 * kk + 1] = y2.y;
+        }
+      }
+      dAacc[n] += gs2.x + gs2.y;  // this row's share of dA[n ^ m]
+      // ---- row reduction: select-free butterflies over the permuted slots ----
+      if ((n & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K0[i] = V[i];
+      } else if ((n & 3) == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K0[i] = __fadd2_rn(K0[i], shfl_xor2(V[i], 1));
+      } else if ((n & 3) == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K1[i] = V[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K1[i] = __fadd2_rn(K1[i], shfl_xor2(V[i], 1));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) K0[i] = __fadd2_rn(K0[i], shfl_xor2(K1[i], 2));
+        // K0 = state 4q + m summed over the lane quad; split the 16 values over the other three lane bits
+        float2 X[4], Y[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          X[i] = __fadd2_rn(sel2(p2, K0[4 + i], K0[i]), shfl_xor2(sel2(p2, K0[i], K0[4 + i]), 4));
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          Y[i] = __fadd2_rn(sel2(p3, X[2 + i], X[i]), shfl_xor2(sel2(p3, X[i], X[2 + i]), 8));
+        const float2 Z = __fadd2_rn(sel2(p4, Y[1], Y[0]), shfl_xor2(sel2(p4, Y[0], Y[1]), 16));
+        stg64_or_red(reinterpret_cast<float*>(dGq), Z.x, Z.y, kSingle);
+        dGq += Lq;
+      }
+    }
+    __syncwarp();  // every lane is done with B/C stage s
+    if (lane == 0 && jb - 2 >= j_lo) issue_bc(jb - 2, s);
+
+    // ---- per-(row, t) epilogue of the block ----
+    const long tpos = (long)jb * kFine;
+    float outv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) outv[i] = fmaf(dl[i], sB[i], Dv * dy[i]);  // du
+    stg_items<T, 8>(reinterpret_cast<T*>(a.du) + rowg * a.L, outv, tpos, a.L, true);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float gd = fmaf(uu[i], sB[i], ddl[i]);  // d loss / d dl
+      if (a.softplus) gd *= sigmoid_from_softplus(dl[i]);
+      outv[i] = gd;
+      db_acc += gd;
+      dD_acc = fmaf(dy[i], uu[i], dD_acc);
+    }
+    stg_items<T, 8>(reinterpret_cast<T*>(a.ddelta) + rowg * a.L, outv, tpos, a.L, true);
+    if constexpr (kHasZ) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) outv[i] = dzf[i] * yv[i];
+      stg_items<T, 8>(reinterpret_cast<T*>(a.dz) + rowg * a.L, outv, tpos, a.L, true);
+    }
+  }
+  // (dim)-shaped sums: over batch and chunks with fp32 atomics
+#pragma unroll
+  for (int s = 0; s < kMaxState; ++s) atomicAdd(a.dA + (long)d * kMaxState + (s ^ m), dAacc[s]);
   if (a.dD) atomicAdd(a.dD + d, dD_acc);
   if (a.dbias) atomicAdd(a.dbias + d, db_acc);
 }
