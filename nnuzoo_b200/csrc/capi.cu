@@ -340,12 +340,13 @@ static bool rl_shape_ok(const NzScanDesc* d) {
   if (!d || d->batch < 1 || d->dim < 1 || d->ngroups < 1 || d->seqlen < 1 || d->dim % d->ngroups) return false;
   if (d->force_generic || d->dstate != NZ_MAX_DSTATE || (d->dim / d->ngroups) % 32 != 0) return false;
   if (getenv("NZ_NO_RL")) return false;
-  // Measured old (warp-scan, chained) vs row-per-lane over the M2Net shapes (profiles/r02_rl_table.log): the
-  // row-per-lane backward wins from about 25 M elements up (-8 .. -21 %) and is the only chunk-parallel backward
-  // (batch-1 inference shape 3.8 -> 1.4 ms); below that its three launches and the aggregate pass cost more than they
-  // save (12 x 128 x 4096: 0.27 vs 0.19 ms).
+  // Measured old (warp-scan, chained) vs row-per-lane over the M2Net shapes (profiles/r02_rl_table.log, butterfly
+  // backward + 32-byte stores): the row-per-lane backward wins from about 12 M elements up (12 x 256 x 4096: 0.30 vs
+  // 0.34 ms, 12 x 128 x 65536: 1.82 vs 2.73 ms) and is the only chunk-parallel backward (batch-1 inference shape
+  // 3.5 -> 1.1 ms); below that its three launches and the aggregate pass cost more than they save (12 x 128 x 4096:
+  // 0.23 vs 0.19 ms).
   {
-    long min_elts = 24L << 20;
+    long min_elts = 12L << 20;
     if (const char* e = getenv("NZ_RL_MIN_ELTS")) min_elts = atol(e);  // tests / tuning
     if ((long)d->batch * d->dim * d->seqlen < min_elts) return false;
   }
@@ -429,11 +430,16 @@ static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
   r.batch = d->batch; r.dim = d->dim; r.ngroups = d->ngroups; r.dpg = d->dim / d->ngroups;
   r.nrb = r.dpg / 32;
   r.ntl = (int)(L * (int64_t)esize(d->dtype) / 128);
-  rl_plan(d, &r.nchunks, &r.tpc);
-  r.softplus = d->delta_softplus;
-  r.single = r.nrb == 1;
+  {
+    auto a32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
+    r.wide = a32(d->du) && a32(d->ddelta) && (!d->dz || a32(d->dz)) && (L * (int64_t)esize(d->dtype)) % 32 == 0;
+    if (getenv("NZ_RL_NOWIDE")) r.wide = 0;
+  }
   r.v2 = 1;
   if (const char* e = getenv("NZ_RL_BWD2")) r.v2 = atoi(e) != 0;  // A/B against the slab version
+  rl_plan(d, &r.nchunks, &r.tpc, r.v2 ? NZ_RL_BWD2_MINB : 12);
+  r.softplus = d->delta_softplus;
+  r.single = r.nrb == 1;
   if (r.nchunks > 1) {
     const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
     char* base = reinterpret_cast<char*>(d->workspace) + nz_scan_workspace_bytes(d);
@@ -480,6 +486,14 @@ static cudaError_t run_fwd_rl(const NzScanDesc* d, cudaStream_t st) {
   r.batch = d->batch; r.dim = d->dim; r.ngroups = d->ngroups; r.dpg = d->dim / d->ngroups;
   r.nrb = r.dpg / 32;
   r.ntl = (int)(L * (int64_t)esize(d->dtype) / 128);
+  {
+    auto a32 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; };
+    const int64_t eo = r.out_f32 ? 4 : (int64_t)esize(d->dtype);
+    r.wide = a32(d->out) && (d->out_stride[0] * eo) % 32 == 0 && (d->out_stride[1] * eo) % 32 == 0 && (!d->xf || a32(d->xf));
+    if (getenv("NZ_RL_NOWIDE")) r.wide = 0;
+  }
+  r.v2f = 0;
+  if (const char* e = getenv("NZ_RL_FWD2")) r.v2f = atoi(e) != 0;  // A/B against the first version
   rl_plan(d, &r.nchunks, &r.tpc, 16);
   r.softplus = d->delta_softplus;
   if (r.nchunks > 1) {
@@ -495,14 +509,13 @@ static cudaError_t run_fwd_rl(const NzScanDesc* d, cudaStream_t st) {
 }
 
 static bool rl_fwd_usable(const NzScanDesc* d) {
-  // Measured (profiles/r02_rl_table.log): without fine checkpoints the warp-scan forward is as fast or faster on every
-  // shape; with them (training) this one wins while a row is at most 256 KB (12 x 128 x 65536: 1.16 vs 1.35 ms,
-  // 12 x 256 x 65536: 2.21 vs 2.46) and loses beyond (12 x 128 x 262144: 5.71 vs 5.34 ms: its 32-byte boxes at a 1 MB
-  // row pitch).  NZ_RL_FWD=0 / 1 forces the choice.
+  // Measured (profiles/r02_rl_table.log): without fine checkpoints the warp-scan forward is as fast or faster on most
+  // shapes; with them (training) the row-per-lane forward wins from about 24 M elements up (12 x 128 x 262144: 4.68 vs
+  // 5.29 ms, 12 x 128 x 65536: 1.07 vs 1.33, 12 x 128 x 16384: 0.35 vs 0.36).  NZ_RL_FWD=0 / 1 forces the choice.
   if (!rl_shape_ok(d)) return false;
   if (const char* on = getenv("NZ_RL_FWD")) {
     if (atoi(on) == 0) return false;
-  } else if (!d->xf || d->seqlen * (int64_t)esize(d->dtype) > (256 << 10)) {
+  } else if (!d->xf || (long)d->batch * d->dim * d->seqlen < (24L << 20)) {
     return false;
   }
   const size_t eo = (d->out_f32 && d->dtype != NZ_F32) ? 4 : esize(d->dtype);

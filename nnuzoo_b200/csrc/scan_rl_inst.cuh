@@ -55,6 +55,7 @@ template <typename T, bool kHasZ>
 static cudaError_t launch_rl_fwd_one(const RlArgs& a, cudaStream_t st) {
   auto agg = scan_rl_agg_kernel<T, false, true>;
   auto maink = scan_fwd_rl_kernel<T, kHasZ>;
+  auto maink2 = scan_fwd_rl2_kernel<T, kHasZ>;
   constexpr size_t agg_smem = 1024 + 2 * (2 * RlCfg<T>::ROWT + RlCfg<T>::BCT) + 64;
   constexpr size_t main_smem = RlFwdSmem<T, kHasZ>::bytes();
   static bool configured = false;
@@ -62,6 +63,8 @@ static cudaError_t launch_rl_fwd_one(const RlArgs& a, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(agg, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(maink, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(maink2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     configured = true;
   }
@@ -72,7 +75,10 @@ static cudaError_t launch_rl_fwd_one(const RlArgs& a, cudaStream_t st) {
     scan_rl_combine_kernel<<<(unsigned)((nrows * kMaxState + 127) / 128), 128, 0, st>>>(a.aggG, a.aggQ, a.Rin, nrows,
                                                                                       a.nchunks, 1);
   }
-  maink<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
+  if (a.v2f)
+    maink2<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
+  else
+    maink<<<(unsigned)(rbt * a.nchunks), 32, main_smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -61,6 +61,8 @@ struct alignas(64) RlArgs {
   int single;    // one warp owns each dB / dC element (dpg == 32): plain stores instead of RED
   unsigned zero; // always 0 (see order_after)
   int v2;        // backward main pass: 1 = butterfly version (scan_bwd_rl2_kernel), 0 = slab version
+  int wide;      // every fp32 output row / checkpoint run is 32-byte aligned: one 32-byte store per block
+  int v2f;       // forward main pass: 1 = pipelined version (scan_fwd_rl2_kernel)
 };
 
 // ---- exp2 on the FMA pipe ----
@@ -136,6 +138,25 @@ __device__ __forceinline__ float2 lds64(uint32_t a) {
   asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
   return v;
 }
+// A lane's 8 results of one block go out as ONE 32-byte store when they are fp32 (st.global.v8.f32, sm_100: STG.E.ENL2.256):
+// two 16-byte stores write every 32-byte sector in halves, and the L2 then spends two partial-sector writes on it -- the
+// forward main pass sat at 69 % L2 throughput with 2 sector writes per sector of data (profiles/r02_kernel_tuning.md).
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+template <typename T>
+__device__ __forceinline__ void stg_blk8(T* row, const float (&v)[8], long t0, long L, bool wide) {
+  if constexpr (sizeof(T) == 4) {
+    if (wide) {
+      stg256(reinterpret_cast<float*>(row) + t0, v);
+      return;
+    }
+  }
+  stg_items<T, 8>(row, v, t0, L, true);
+}
+
 // a lane's 8 items of block `blk` out of a swizzled [rows][128 B] tile; row = tile row (lane for row tiles, the state
 // for B / C tiles -- then every lane reads the same address: a broadcast)
 template <typename T>
@@ -247,7 +268,7 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
         if (a.softplus) x = softplus_f(x);
         dlsum += x;
         if (kFwd) dy[i] *= x;  // dl_t u_t
-        dl[i] = fminf(fmaxf(x, -dlim), dlim);
+        dl[i] = NZ_RL_POLY_AGG > 0 ? fminf(fmaxf(x, -dlim), dlim) : x;
       }
 #pragma unroll
       for (int n = 0; n < kMaxState; ++n) {
@@ -614,7 +635,7 @@ __global__ void __launch_bounds__(32, NZ_RL_BWD_MINB) scan_bwd_rl_kernel(const _
     float outv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) outv[i] = fmaf(dl[i], sB[i], Dv * dy[i]);  // du
-    stg_items<T, 8>(reinterpret_cast<T*>(a.du) + rowg * a.L, outv, tpos, a.L, true);
+    stg_blk8<T>(reinterpret_cast<T*>(a.du) + rowg * a.L, outv, tpos, a.L, a.wide);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float gd = fmaf(uu[i], sB[i], ddl[i]);  // d loss / d dl
@@ -623,11 +644,11 @@ __global__ void __launch_bounds__(32, NZ_RL_BWD_MINB) scan_bwd_rl_kernel(const _
       db_acc += gd;
       dD_acc = fmaf(dy[i], uu[i], dD_acc);
     }
-    stg_items<T, 8>(reinterpret_cast<T*>(a.ddelta) + rowg * a.L, outv, tpos, a.L, true);
+    stg_blk8<T>(reinterpret_cast<T*>(a.ddelta) + rowg * a.L, outv, tpos, a.L, a.wide);
     if constexpr (kHasZ) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) outv[i] = dzf[i] * yv[i];
-      stg_items<T, 8>(reinterpret_cast<T*>(a.dz) + rowg * a.L, outv, tpos, a.L, true);
+      stg_blk8<T>(reinterpret_cast<T*>(a.dz) + rowg * a.L, outv, tpos, a.L, a.wide);
     }
   }
   // (dim)-shaped sums: over batch and chunks with fp32 atomics
@@ -666,8 +687,11 @@ struct RlMain2Smem {
   static constexpr size_t bytes() { return 1024 + TOTAL; }
 };
 
+// Resident warps per SM the butterfly pass is compiled for.  Its natural register demand is 249: at 12 warps (168
+// registers) it spills 224 bytes per lane and runs 2.07 ms on 12 x 128 x 65536, at 8 warps (no spills) 1.88 ms, at 14 / 16
+// warps (128 registers) 2.6 - 2.7 ms (profiles/r02_kernel_tuning.md).
 #ifndef NZ_RL_BWD2_MINB
-#define NZ_RL_BWD2_MINB 12
+#define NZ_RL_BWD2_MINB 8
 #endif
 
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int mask) {
@@ -687,8 +711,13 @@ __device__ __forceinline__ void lds_bc2(uint32_t base, int q, float (&v)[8]) {
   }
 }
 
+#ifdef NZ_RL_BWD2_MAXREG  // tuning: an explicit register cap instead of a residency target
+#define NZ_RL_BWD2_BOUNDS __maxnreg__(NZ_RL_BWD2_MAXREG)
+#else
+#define NZ_RL_BWD2_BOUNDS __launch_bounds__(32, NZ_RL_BWD2_MINB)
+#endif
 template <typename T, bool kHasZ, bool kSingle>
-__global__ void __launch_bounds__(32, NZ_RL_BWD2_MINB) scan_bwd_rl2_kernel(const __grid_constant__ RlArgs a) {
+__global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ RlArgs a) {
   using Cfg = RlCfg<T>;
   using SM = RlMain2Smem<T, kHasZ>;
   constexpr int NBLK = Cfg::NBLK, RB = SM::RB, BB = SM::BB;
@@ -935,7 +964,7 @@ __global__ void __launch_bounds__(32, NZ_RL_BWD2_MINB) scan_bwd_rl2_kernel(const
     float outv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) outv[i] = fmaf(dl[i], sB[i], Dv * dy[i]);  // du
-    stg_items<T, 8>(reinterpret_cast<T*>(a.du) + rowg * a.L, outv, tpos, a.L, true);
+    stg_blk8<T>(reinterpret_cast<T*>(a.du) + rowg * a.L, outv, tpos, a.L, a.wide);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float gd = fmaf(uu[i], sB[i], ddl[i]);  // d loss / d dl
@@ -944,11 +973,11 @@ __global__ void __launch_bounds__(32, NZ_RL_BWD2_MINB) scan_bwd_rl2_kernel(const
       db_acc += gd;
       dD_acc = fmaf(dy[i], uu[i], dD_acc);
     }
-    stg_items<T, 8>(reinterpret_cast<T*>(a.ddelta) + rowg * a.L, outv, tpos, a.L, true);
+    stg_blk8<T>(reinterpret_cast<T*>(a.ddelta) + rowg * a.L, outv, tpos, a.L, a.wide);
     if constexpr (kHasZ) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) outv[i] = dzf[i] * yv[i];
-      stg_items<T, 8>(reinterpret_cast<T*>(a.dz) + rowg * a.L, outv, tpos, a.L, true);
+      stg_blk8<T>(reinterpret_cast<T*>(a.dz) + rowg * a.L, outv, tpos, a.L, a.wide);
     }
   }
   // (dim)-shaped sums: over batch and chunks with fp32 atomics
@@ -977,8 +1006,11 @@ struct RlFwdSmem {
   static constexpr size_t bytes() { return 1024 + TOTAL; }
 };
 
+#ifndef NZ_RL_FWD_MINB
+#define NZ_RL_FWD_MINB 16
+#endif
 template <typename T, bool kHasZ>
-__global__ void __launch_bounds__(32, 16) scan_fwd_rl_kernel(const __grid_constant__ RlArgs a) {
+__global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const __grid_constant__ RlArgs a) {
   using SM = RlFwdSmem<T, kHasZ>;
   constexpr int NBLK = RlCfg<T>::NBLK, RB = SM::RB, BB = SM::BB;
   constexpr int BPC = NZ_CHUNK / kFine;  // fine blocks per coarse checkpoint
@@ -1054,7 +1086,7 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_rl_kernel(const __grid_consta
       if (a.softplus) x = softplus_f(x);
       y[i] = Dv * dlu[i];
       dlu[i] = x * dlu[i];
-      dl[i] = fminf(fmaxf(x, -dlim), dlim);  // from here on dl only feeds the exponents
+      dl[i] = NZ_RL_POLY_FWD > 0 ? fminf(fmaxf(x, -dlim), dlim) : x;  // from here on dl only feeds the exponents
     }
     mbar_wait(&bars[2 + s], ph);
     const uint32_t tB = smem_s + SM::OFF_BC + s * SM::BSTAGE, tC = tB + BB;
@@ -1091,19 +1123,206 @@ __global__ void __launch_bounds__(32, 16) scan_fwd_rl_kernel(const __grid_consta
     }
     const long tpos = (long)jb * kFine;
     if (sizeof(T) == 2 && a.out_f32)
-      stg_items<float, 8>(reinterpret_cast<float*>(a.out) + orow, y, tpos, a.L, true);
+      stg_blk8<float>(reinterpret_cast<float*>(a.out) + orow, y, tpos, a.L, a.wide);
     else
-      stg_items<T, 8>(reinterpret_cast<T*>(a.out) + orow, y, tpos, a.L, true);
+      stg_blk8<T>(reinterpret_cast<T*>(a.out) + orow, y, tpos, a.L, a.wide);
     // checkpoints: h at the end of the block
     if (a.xfw) {
-      float4* xo = reinterpret_cast<float4*>(a.xfw + (rowg * nbt + jb) * kMaxState);
+      float* xo = a.xfw + (rowg * nbt + jb) * kMaxState;
+      if (a.wide) {
+        stg256(xo, &h[0]);
+        stg256(xo + 8, &h[8]);
+      } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) xo[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(xo)[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      }
     }
     if ((jb + 1) % BPC == 0 || jb + 1 == nbt) {
       float4* xo = reinterpret_cast<float4*>(a.x + (rowg * a.nck + jb / BPC) * kMaxState);
 #pragma unroll
       for (int q = 0; q < 4; ++q) xo[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    }
+  }
+}
+
+// ================================================================================================
+// Forward main pass, pipelined version
+// ================================================================================================
+// Same decomposition as scan_fwd_rl_kernel; two changes aimed at the MUFU pipe's idle time (61 % busy there, top stall
+// samples on the first use of every shared-memory load: profiles/r02_kernel_tuning.md):
+//   * B / C rows of state n + 1 are requested before the math of state n (double-buffered registers);
+//   * the row operands of block j + 1 are read, softplus'ed and multiplied in the middle of block j's state loop, so a
+//     block no longer starts with a serial mbarrier wait -> LDS -> ex2 -> lg2 chain; the row ring therefore runs two
+//     blocks ahead of the B / C ring.
+#ifndef NZ_RL_FWD2_MINB
+#define NZ_RL_FWD2_MINB 12
+#endif
+template <typename T, bool kHasZ>
+__global__ void __launch_bounds__(32, NZ_RL_FWD2_MINB) scan_fwd_rl2_kernel(const __grid_constant__ RlArgs a) {
+  using SM = RlFwdSmem<T, kHasZ>;
+  constexpr int NBLK = RlCfg<T>::NBLK, RB = SM::RB, BB = SM::BB;
+  constexpr int BPC = NZ_CHUNK / kFine;  // fine blocks per coarse checkpoint
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::OFF_BARS);  // [0],[1] row stages, [2],[3] B/C stages
+  const uint32_t smem_s = keep(smem_u32(smem));
+  const int lane = threadIdx.x;
+
+  const int item = blockIdx.x;
+  const int c = item % a.nchunks;
+  int w = item / a.nchunks;
+  const int rb = w % a.nrb;
+  w /= a.nrb;
+  const int g = w % a.ngroups, b = w / a.ngroups;
+  const int d0 = g * a.dpg + rb * 32, d = d0 + lane;
+  const long rowg = (long)b * a.dim + d;
+  const int t_lo = c * a.tpc, t_hi = min(a.ntl, t_lo + a.tpc);
+  const int j_lo = t_lo * NBLK, j_hi = t_hi * NBLK;
+  const long nbt = a.L / kFine;
+
+  auto issue_rows = [&](int j, int s) {
+    uint8_t* st = smem + s * SM::RSTAGE;
+    mbar_arrive_expect_tx(&bars[s], SM::NROWT * RB);
+    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, d0, b);
+    tma_load_4d(st + RB, &a.tm_delta, &bars[s], 0, j, d0, b);
+    if (kHasZ) tma_load_4d(st + 2 * RB, &a.tm_z, &bars[s], 0, j, d0, b);
+  };
+  auto issue_bc = [&](int j, int s) {
+    uint8_t* sb = smem + SM::OFF_BC + s * SM::BSTAGE;
+    mbar_arrive_expect_tx(&bars[2 + s], 2 * BB);
+    tma_load_5d(sb, &a.tm_B, &bars[2 + s], 0, j, 0, g, b);
+    tma_load_5d(sb + BB, &a.tm_C, &bars[2 + s], 0, j, 0, g, b);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+    issue_rows(j_lo, 0);
+    issue_bc(j_lo, 0);
+    if (j_lo + 1 < j_hi) {
+      issue_rows(j_lo + 1, 1);
+      issue_bc(j_lo + 1, 1);
+    }
+  }
+  __syncwarp();
+  float A2[kMaxState], h[kMaxState];
+  {
+    const float* hin = a.Rin + (rowg * a.nchunks + c) * kMaxState;
+#pragma unroll
+    for (int n = 0; n < kMaxState; ++n) {
+      A2[n] = __ldg(a.A + (long)d * a.A_ds + n) * kLog2e;
+      h[n] = a.nchunks > 1 ? __ldg(hin + n) : 0.f;
+    }
+  }
+  const float Dv = a.D ? __ldg(a.D + d) : 0.f;
+  const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
+  const long orow = (long)b * a.o_bs + (long)d * a.o_ds;
+
+  float dl[8], dlu[8], y[8];
+  [[maybe_unused]] float zz[kHasZ ? 8 : 1];
+  // row operands of the block whose rows sit in stage s -> (dl, dl u, D u, z)
+  auto prologue = [&](int s, float (&pdl)[8], float (&pdlu)[8], float (&py)[8], float (&pz)[kHasZ ? 8 : 1]) {
+    const uint32_t rst = smem_s + s * SM::RSTAGE;
+    lds_blockrow<T>(rst, lane, pdlu);  // u for now
+    lds_blockrow<T>(rst + RB, lane, pdl);
+    if constexpr (kHasZ) lds_blockrow<T>(rst + 2 * RB, lane, pz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float x = pdl[i] + bias;
+      if (a.softplus) x = softplus_f(x);
+      py[i] = Dv * pdlu[i];
+      pdlu[i] = x * pdlu[i];
+      pdl[i] = x;
+    }
+  };
+  mbar_wait(&bars[0], 0);
+  prologue(0, dl, dlu, y, zz);
+  __syncwarp();
+  if (lane == 0 && j_lo + 2 < j_hi) issue_rows(j_lo + 2, 0);
+
+  int k = 0;
+#pragma unroll 1
+  for (int jb = j_lo; jb < j_hi; ++jb, ++k) {
+    const int s = k & 1;
+    const uint32_t ph = (uint32_t)(k >> 1) & 1u;
+    mbar_wait(&bars[2 + s], ph);
+    const uint32_t tB = smem_s + SM::OFF_BC + s * SM::BSTAGE, tC = tB + BB;
+    float ndl[8], ndlu[8], ny[8];
+    [[maybe_unused]] float nz[kHasZ ? 8 : 1];
+    float bcv[2][2][8];
+    lds_bc<T>(tB, 0, bcv[0][0]);
+    lds_bc<T>(tC, 0, bcv[0][1]);
+#pragma unroll
+    for (int n = 0; n < kMaxState; ++n) {
+      float (&bv)[8] = bcv[n & 1][0];
+      float (&cv)[8] = bcv[n & 1][1];
+      if (n + 1 < kMaxState) {
+        lds_bc<T>(tB, n + 1, bcv[(n + 1) & 1][0]);
+        lds_bc<T>(tC, n + 1, bcv[(n + 1) & 1][1]);
+      }
+      if (n == kMaxState / 2 && jb + 1 < j_hi) {
+        // next block's row operands (stage s ^ 1 of the row ring, phase of block k + 1)
+        mbar_wait(&bars[s ^ 1], (uint32_t)((k + 1) >> 1) & 1u);
+        prologue(s ^ 1, ndl, ndlu, ny, nz);
+        __syncwarp();
+        if (lane == 0 && jb + 3 < j_hi) issue_rows(jb + 3, s ^ 1);
+      }
+      float hh[8];
+      float hc = h[n];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 x2 = mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n]));
+        const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
+        hc = fmaf(ex2_approx(x2.x), hc, b2.x);
+        hh[2 * kk] = hc;
+        hc = fmaf(ex2_approx(x2.y), hc, b2.y);
+        hh[2 * kk + 1] = hc;
+      }
+      h[n] = hc;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        float2 y2 = f2(y[2 * kk], y[2 * kk + 1]);
+        y2 = fma2(f2(cv[2 * kk], cv[2 * kk + 1]), f2(hh[2 * kk], hh[2 * kk + 1]), y2);
+        y[2 * kk] = y2.x;
+        y[2 * kk + 1] = y2.y;
+      }
+    }
+    // every lane is done with this block's B / C stage: request the block after the next one
+    __syncwarp();
+    if (lane == 0 && jb + 2 < j_hi) issue_bc(jb + 2, s);
+    if constexpr (kHasZ) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] *= zz[i] * sigmoid_f(zz[i]);
+    }
+    const long tpos = (long)jb * kFine;
+    if (sizeof(T) == 2 && a.out_f32)
+      stg_blk8<float>(reinterpret_cast<float*>(a.out) + orow, y, tpos, a.L, a.wide);
+    else
+      stg_blk8<T>(reinterpret_cast<T*>(a.out) + orow, y, tpos, a.L, a.wide);
+    // checkpoints: h at the end of the block
+    if (a.xfw) {
+      float* xo = a.xfw + (rowg * nbt + jb) * kMaxState;
+      if (a.wide) {
+        stg256(xo, &h[0]);
+        stg256(xo + 8, &h[8]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          reinterpret_cast<float4*>(xo)[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      }
+    }
+    if ((jb + 1) % BPC == 0 || jb + 1 == nbt) {
+      float4* xo = reinterpret_cast<float4*>(a.x + (rowg * a.nck + jb / BPC) * kMaxState);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) xo[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dl[i] = ndl[i];
+      dlu[i] = ndlu[i];
+      y[i] = ny[i];
+      if constexpr (kHasZ) zz[i] = nz[i];
     }
   }
 }
