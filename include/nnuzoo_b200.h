@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NZ_ABI_VERSION 3
+#define NZ_ABI_VERSION 4
 
 /* element types of u / delta / B / C / z / out / dout / du / ddelta / dz */
 #define NZ_F32 0
@@ -120,6 +120,18 @@ typedef struct NzScanDesc {
                                qualifies (nz_scan_fine_bytes() > 0; ignored otherwise); nz_scan_bwd given the same buffer
                                (and a workspace of nz_scan_workspace_bytes_bwd() bytes) runs the row-per-lane backward,
                                otherwise the warp-scan backward that only needs x. */
+
+  /* ---- folded SS2D directions (ABI v4; both 0 for a plain selective_scan_fn call) ----
+   * SS2D's CrossScan (m2net.py:175-177) feeds the scan x row-major, x column-major and the L-flips of both.  A flipped
+   * direction is the same recurrence run from t = L-1 down to 0 over the UN-flipped arrays, so the flipped copies need
+   * not exist: rev_mask bit g makes group g walk the sequence backwards (u, delta, B, C, z are read and out, du, ddelta,
+   * dB, dC are written at their un-flipped positions; last_state / x then describe t = 0), and u_gdiv = 2 lets the
+   * forward and the backward walker of one array share its rows.  Needs the row-per-lane kernels: d_state 16, groups of
+   * a multiple of 32 rows, TMA-expressible operands, xf and the nz_scan_workspace_bytes_bwd() scratch in BOTH
+   * directions; NZ_EUNSUPPORTED otherwise. */
+  int32_t rev_mask;         /* bit g (g < 32): group g runs reversed in time */
+  int32_t u_gdiv;           /* 0 / 1: u is (batch, dim, L).  n > 1: u is (batch, dim / n, L) and group g reads the rows of
+                               group g / n (u_stride[1] is still the row stride); ngroups % n == 0 */
 } NzScanDesc;
 
 /* Bytes of scratch a call with this batch / dim needs (same for forward and backward). */
@@ -175,6 +187,17 @@ int nz_cross_merge(const float* out_y, float* y, int32_t batch, int32_t dim, int
  * nz_cross_scan is nz_cross_merge with mode 1, so it needs no entry point of its own.) */
 int nz_cross_merge_bwd(const float* dy, float* d_out_y, int32_t batch, int32_t dim, int32_t nspatial,
                        const int64_t* spatial, int32_t mode, void* stream);
+
+/*
+ * Folded 2-D CrossScan (the data-movement half of nz_ss2d below): x (batch, dim, H, W) -> xs2 (batch, 2, dim, L) =
+ * {row-major walk (a copy), column-major walk}.  The two L-flipped directions of m2net.py:176 are not materialised: the
+ * scan walks these two arrays backwards (NzScanDesc::rev_mask).  nz_cross_merge_pair is the adjoint:
+ * dx[p] = dxs2[:, 0][p] + dxs2[:, 1][t(p)] (one fp32 add, rounded to dtype).
+ */
+int nz_cross_scan_pair(const void* x, void* xs2, int32_t dtype, int32_t batch, int32_t dim, int32_t H, int32_t W,
+                       void* stream);
+int nz_cross_merge_pair(const void* dxs2, void* dx, int32_t dtype, int32_t batch, int32_t dim, int32_t H, int32_t W,
+                        void* stream);
 
 /*
  * Depthwise causal conv1d (+ SiLU) of the 1-D Mamba block: out[b,d,l] = act(bias[d] + sum_k w[d,k] x[b,d,l-(W-1)+k])
@@ -261,6 +284,18 @@ int nz_ss2d_epilogue_bwd(const void* dout, const float* y_merged, const float* m
                          const int64_t* z_stride, const float* gamma, const float* beta, void* d_out_y, void* dz,
                          float* dgamma, float* dbeta, int32_t z_dtype, int32_t out_dtype, int32_t grad_dtype,
                          int32_t batch, int32_t D, int32_t H, int32_t W, void* stream);
+
+/* The same two kernels on the FOLDED direction layout: out_y / d_out_y (batch, 4, D, L) hold {row-major forward, row-major
+ * backward, column-major forward, column-major backward}, none of them flipped -- what nz_scan_fwd / nz_scan_bwd write and
+ * read with ngroups = 4, rev_mask = 0b1010, u_gdiv = 2 over xs2 of nz_cross_scan_pair.  Sum order unchanged:
+ * ((y[0] + y[1]) + T y[2]) + T y[3] = ((y0 + flip y2) + T y1) + T flip y3 of m2net.py:202-206, :218, bit for bit. */
+int nz_ss2d_epilogue_fwd_folded(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma,
+                                const float* beta, void* out, float* y_merged, float* mean, float* rstd, int32_t z_dtype,
+                                int32_t out_dtype, int32_t batch, int32_t D, int32_t H, int32_t W, float eps, void* stream);
+int nz_ss2d_epilogue_bwd_folded(const void* dout, const float* y_merged, const float* mean, const float* rstd, const void* z,
+                                const int64_t* z_stride, const float* gamma, const float* beta, void* d_out_y, void* dz,
+                                float* dgamma, float* dbeta, int32_t z_dtype, int32_t out_dtype, int32_t grad_dtype,
+                                int32_t batch, int32_t D, int32_t H, int32_t W, void* stream);
 
 /*
  * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("NNUZOO_B200_LIB") or os.path.join(_HERE, "lib", "libn
 NZ_F32, NZ_BF16, NZ_F16 = 0, 1, 2
 NZ_CHUNK = int(os.environ.get("NNUZOO_B200_CHUNK", "128"))   # tuning builds may use another interval
 NZ_MAX_DSTATE = 16
-ABI_VERSION = 3
+ABI_VERSION = 4
 NZ_FINE = 8  # steps between two fine checkpoints (NzScanDesc.xf)
 WS_HEADER = 256
 
@@ -42,6 +42,7 @@ class NzScanDesc(ctypes.Structure):
         ("ddelta_bias", _vp),
         ("workspace", _vp), ("workspace_bytes", _i64),
         ("xf", _vp),
+        ("rev_mask", _i32), ("u_gdiv", _i32),
     ]
 
 
@@ -124,6 +125,12 @@ def lib():
                 L.nz_ss2d_epilogue_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.POINTER(_i64), _vp, _vp, _vp, _vp, _vp,
                                                    _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
                 L.nz_ss2d_epilogue_bwd.restype = ctypes.c_int
+                for name in ("nz_ss2d_epilogue_fwd", "nz_ss2d_epilogue_bwd"):
+                    getattr(L, name + "_folded").argtypes = getattr(L, name).argtypes
+                    getattr(L, name + "_folded").restype = ctypes.c_int
+                for name in ("nz_cross_scan_pair", "nz_cross_merge_pair"):
+                    getattr(L, name).argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
+                    getattr(L, name).restype = ctypes.c_int
                 L.nz_sizeof_conv1d_desc.restype = _i64
                 if L.nz_sizeof_conv1d_desc() != ctypes.sizeof(NzConv1dDesc):
                     raise NativeLibraryError("NzConv1dDesc layout differs between _native.py and the .so")

@@ -111,3 +111,43 @@ def cross_merge(out_y: torch.Tensor, spatial, mode: str = "reference") -> torch.
     mode="reference" reproduces ssnd2net.py:291-298 bit-exactly in 3-D (directions 2 and 5 unused);
     mode="fixed" un-permutes direction 2 / 5 from their own order (never used for parity)."""
     return CrossMergeFn.apply(out_y, tuple(int(s) for s in spatial), {"reference": 0, "fixed": 1}[mode])
+
+
+class CrossScanPairFn(torch.autograd.Function):
+    """x (B, D, H, W) -> xs2 (B, 2, D, L) = {row-major walk, column-major walk}: the two arrays SS2D's four directions
+    walk (m2net.py:175-177); the L-flipped directions are walked backwards by the scan itself (``rev_mask``) instead of
+    being materialised.  Backward = nz_cross_merge_pair."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _need_cuda(x, "cross_scan_pair")
+        if x.dtype not in _DTYPES or x.dim() != 4:
+            raise TypeError("cross_scan_pair expects a (B, D, H, W) fp32 / bf16 / fp16 tensor")
+        x = x.contiguous()
+        b, d, H, W = x.shape
+        xs2 = torch.empty((b, 2, d, H * W), dtype=x.dtype, device=x.device)
+        _native.bind_device(x.device.index)
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().nz_cross_scan_pair(
+                ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(xs2.data_ptr()), _DTYPES[x.dtype], b, d, H, W,
+                _stream(x.device)), "nz_cross_scan_pair")
+        ctx.hw = (H, W)
+        return xs2
+
+    @staticmethod
+    def backward(ctx, dxs2):
+        H, W = ctx.hw
+        dxs2 = dxs2.contiguous()
+        b, _, d, _ = dxs2.shape
+        dx = torch.empty((b, d, H, W), dtype=dxs2.dtype, device=dxs2.device)
+        _native.bind_device(dxs2.device.index)
+        with torch.cuda.device(dxs2.device):
+            _native.check(_native.lib().nz_cross_merge_pair(
+                ctypes.c_void_p(dxs2.data_ptr()), ctypes.c_void_p(dx.data_ptr()), _DTYPES[dxs2.dtype], b, d, H, W,
+                _stream(dxs2.device)), "nz_cross_merge_pair")
+        return dx
+
+
+def cross_scan_pair(x: torch.Tensor) -> torch.Tensor:
+    """x (B, D, H, W) -> (B, 2, D, L): row-major and column-major walks only (see CrossScanPairFn)."""
+    return CrossScanPairFn.apply(x)

@@ -140,6 +140,9 @@ static bool tma_ok_rows(const void* p, int dtype, int64_t L, const int64_t* dims
   return true;
 }
 
+static inline bool folded(const NzScanDesc* d) { return d->rev_mask != 0 || d->u_gdiv > 1; }
+static inline int u_gdiv(const NzScanDesc* d) { return d->u_gdiv > 1 ? d->u_gdiv : 1; }
+
 static int validate(const NzScanDesc* d, bool bwd) {
   if (!d) return fail(NZ_EINVAL, "null descriptor");
   if (d->batch < 1 || d->dim < 1 || d->dstate < 1 || d->ngroups < 1 || d->seqlen < 1)
@@ -162,6 +165,11 @@ static int validate(const NzScanDesc* d, bool bwd) {
     if ((d->z != nullptr) != (d->dz != nullptr)) return fail(NZ_EINVAL, "dz must be given iff z is given");
   }
   if ((long long)d->batch * d->ngroups * d->dim > 2000000000LL) return fail(NZ_EINVAL, "grid too large");
+  if (d->u_gdiv > 1 && d->ngroups % d->u_gdiv)
+    return fail(NZ_EINVAL, "ngroups %d is not a multiple of u_gdiv %d", d->ngroups, d->u_gdiv);
+  if (d->ngroups < 32 && ((unsigned)d->rev_mask >> d->ngroups))
+    return fail(NZ_EINVAL, "rev_mask 0x%x names groups beyond %d", d->rev_mask, d->ngroups);
+  if (d->rev_mask && d->ngroups > 32) return fail(NZ_EUNSUPPORTED, "rev_mask needs ngroups <= 32");
   return NZ_OK;
 }
 
@@ -348,8 +356,9 @@ static bool rl_shape_ok(const NzScanDesc* d) {
   {
     long min_elts = 12L << 20;
     if (const char* e = getenv("NZ_RL_MIN_ELTS")) min_elts = atol(e);  // tests / tuning
-    if ((long)d->batch * d->dim * d->seqlen < min_elts) return false;
+    if (!folded(d) && (long)d->batch * d->dim * d->seqlen < min_elts) return false;  // folded calls have no other path
   }
+  const int64_t ud[2] = {d->dim / u_gdiv(d), d->batch};
   const int64_t rd[2] = {d->dim, d->batch};
   const int64_t us[2] = {d->u_stride[1], d->u_stride[0]};
   const int64_t ds[2] = {d->delta_stride[1], d->delta_stride[0]};
@@ -358,7 +367,7 @@ static bool rl_shape_ok(const NzScanDesc* d) {
   const int64_t bs[3] = {d->B_stride[2], d->B_stride[1], d->B_stride[0]};
   const int64_t cs[3] = {d->C_stride[2], d->C_stride[1], d->C_stride[0]};
   const int64_t L = d->seqlen;
-  if (!tma_ok_rows(d->u, d->dtype, L, rd, us, 2) || !tma_ok_rows(d->delta, d->dtype, L, rd, ds, 2) ||
+  if (!tma_ok_rows(d->u, d->dtype, L, ud, us, 2) || !tma_ok_rows(d->delta, d->dtype, L, rd, ds, 2) ||
       !tma_ok_rows(d->B, d->dtype, L, bd, bs, 3) || !tma_ok_rows(d->C, d->dtype, L, bd, cs, 3))
     return false;
   if (d->z && !tma_ok_rows(d->z, d->dtype, L, rd, zs, 2)) return false;
@@ -411,7 +420,8 @@ static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
   const int64_t nbt = L / NZ_FINE;
   const int64_t xs[2] = {nbt * NZ_MAX_DSTATE, (int64_t)d->dim * nbt * NZ_MAX_DSTATE};
   // main pass: per-block boxes
-  bool ok = make_map_blk(&r.tm_u, d->dtype, d->u, NZ_FINE, nbt, 2, rd, us, rbox) &&
+  const int64_t ud[2] = {d->dim / u_gdiv(d), d->batch};
+  bool ok = make_map_blk(&r.tm_u, d->dtype, d->u, NZ_FINE, nbt, 2, ud, us, rbox) &&
             make_map_blk(&r.tm_delta, d->dtype, d->delta, NZ_FINE, nbt, 2, rd, ds, rbox) &&
             make_map_blk(&r.tm_dout, d->dtype, d->dout, NZ_FINE, nbt, 2, rd, os, rbox) &&
             make_map_blk(&r.tm_B, d->dtype, d->B, NZ_FINE, nbt, 3, bd, bs, bbox) &&
@@ -439,6 +449,8 @@ static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
   if (const char* e = getenv("NZ_RL_BWD2")) r.v2 = atoi(e) != 0;  // A/B against the slab version
   rl_plan(d, &r.nchunks, &r.tpc, r.v2 ? NZ_RL_BWD2_MINB : 12);
   r.softplus = d->delta_softplus;
+  r.rev_mask = d->rev_mask;
+  r.u_gdiv = u_gdiv(d);
   r.single = r.nrb == 1;
   if (r.nchunks > 1) {
     const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
@@ -469,13 +481,14 @@ static cudaError_t run_fwd_rl(const NzScanDesc* d, cudaStream_t st) {
   const int bbox[3] = {NZ_MAX_DSTATE, 1, 1};
   const int tl = 128 / (int)esize(d->dtype);
   const int64_t nbt = L / NZ_FINE;
-  bool ok = make_map_blk(&r.tm_u, d->dtype, d->u, NZ_FINE, nbt, 2, rd, us, rbox) &&
+  const int64_t ud[2] = {d->dim / u_gdiv(d), d->batch};
+  bool ok = make_map_blk(&r.tm_u, d->dtype, d->u, NZ_FINE, nbt, 2, ud, us, rbox) &&
             make_map_blk(&r.tm_delta, d->dtype, d->delta, NZ_FINE, nbt, 2, rd, ds, rbox) &&
             make_map_blk(&r.tm_B, d->dtype, d->B, NZ_FINE, nbt, 3, bd, bs, bbox) &&
             make_map_blk(&r.tm_C, d->dtype, d->C, NZ_FINE, nbt, 3, bd, cs, bbox);
   if (ok && d->z) ok = make_map_blk(&r.tm_z, d->dtype, d->z, NZ_FINE, nbt, 2, rd, zs, rbox);
   ok = ok && make_map(&r.g_delta, d->dtype, d->delta, 2, rd, ds, L, rbox, tl) &&
-       make_map(&r.g_row1, d->dtype, d->u, 2, rd, us, L, rbox, tl) && make_map(&r.g_bc, d->dtype, d->B, 3, bd, bs, L, bbox, tl);
+       make_map(&r.g_row1, d->dtype, d->u, 2, ud, us, L, rbox, tl) && make_map(&r.g_bc, d->dtype, d->B, 3, bd, bs, L, bbox, tl);
   if (!ok) return cudaErrorInvalidValue;
   r.A = d->A; r.D = d->D; r.bias = d->delta_bias;
   r.out = d->out; r.x = d->x; r.xfw = d->xf;
@@ -496,6 +509,8 @@ static cudaError_t run_fwd_rl(const NzScanDesc* d, cudaStream_t st) {
   if (const char* e = getenv("NZ_RL_FWD2")) r.v2f = atoi(e) != 0;  // A/B against the first version
   rl_plan(d, &r.nchunks, &r.tpc, 16);
   r.softplus = d->delta_softplus;
+  r.rev_mask = d->rev_mask;
+  r.u_gdiv = u_gdiv(d);
   if (r.nchunks > 1) {
     const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
     char* base = reinterpret_cast<char*>(d->workspace) + nz_scan_workspace_bytes(d);
@@ -513,7 +528,9 @@ static bool rl_fwd_usable(const NzScanDesc* d) {
   // shapes; with them (training) the row-per-lane forward wins from about 24 M elements up (12 x 128 x 262144: 4.68 vs
   // 5.29 ms, 12 x 128 x 65536: 1.07 vs 1.33, 12 x 128 x 16384: 0.35 vs 0.36).  NZ_RL_FWD=0 / 1 forces the choice.
   if (!rl_shape_ok(d)) return false;
-  if (const char* on = getenv("NZ_RL_FWD")) {
+  if (folded(d)) {
+    // reversed groups / shared u rows exist only in these kernels
+  } else if (const char* on = getenv("NZ_RL_FWD")) {
     if (atoi(on) == 0) return false;
   } else if (!d->xf || (long)d->batch * d->dim * d->seqlen < (24L << 20)) {
     return false;
@@ -536,6 +553,11 @@ static bool rl_bwd_usable(const NzScanDesc* d) {
 static int run_scan(const NzScanDesc* d, void* stream, bool bwd) {
   int rc = validate(d, bwd);
   if (rc) return rc;
+  if (folded(d) && !(bwd ? rl_bwd_usable(d) : rl_fwd_usable(d)))
+    return fail(NZ_EUNSUPPORTED,
+                "rev_mask / u_gdiv need the row-per-lane kernels: d_state 16, groups of a multiple of 32 rows, rows a "
+                "whole number of 128-byte lines, 16-byte aligned operands, the nz_scan_workspace_bytes_bwd() scratch%s",
+                bwd ? " and xf" : "");
   ScanKArgs a;
   fill_args(d, a, bwd);
   if ((long long)a.nrb_total * a.nchunks > 2000000000LL) return fail(NZ_EINVAL, "too many tiles");

@@ -11,6 +11,8 @@
 //        k3..5: same at L-1-l
 // The merge sums in the reference's left-to-right order with separate fp32 adds, so results are
 // bit-identical to the PyTorch expressions.  One thread per output element, writes coalesced.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -232,6 +234,95 @@ __global__ void __launch_bounds__(256) cross_merge2d_tiled_kernel(const float* _
   }
 }
 
+// Folded 2-D CrossScan: only the two ARRAYS the four directions walk -- xs2 (b, 2, d, L) = {x row-major (a copy), x
+// column-major} -- the two flipped directions read them backwards inside the scan (NzScanDesc::rev_mask) instead of
+// getting flipped copies.  Same tiling as above.
+template <typename T>
+__global__ void __launch_bounds__(256) cross_scan2d_pair_kernel(const T* __restrict__ x, T* __restrict__ xs, long planes,
+                                                                int dim, long H, long W, int tiles_w, int tiles_h) {
+  __shared__ T tile[kCT][kCT + 1];
+  const long L = H * W;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (long blk = blockIdx.x;; blk += gridDim.x) {
+    const long plane = blk / ((long)tiles_w * tiles_h);
+    const int tr = (int)(blk % ((long)tiles_w * tiles_h));
+    if (plane >= planes) break;
+    const long h0 = (long)(tr / tiles_w) * kCT, w0 = (long)(tr % tiles_w) * kCT;
+    const long b = plane / dim;
+    const int dd = (int)(plane % dim);
+    const T* src = x + plane * L;
+    T* o0 = xs + ((b * 2 + 0) * dim + dd) * L;
+    T* o1 = xs + ((b * 2 + 1) * dim + dd) * L;
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {
+      const long h = h0 + ty + r, w = w0 + tx;
+      if (h < H && w < W) {
+        const T v = src[h * W + w];
+        tile[ty + r][tx] = v;
+        o0[h * W + w] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {
+      const long w = w0 + ty + r, h = h0 + tx;
+      if (h < H && w < W) o1[w * H + h] = tile[tx][ty + r];
+    }
+    __syncthreads();
+  }
+}
+
+// its adjoint: dxs2 (b, 2, d, L) -> dx (b, d, L) = dxs2[:, 0][p] + dxs2[:, 1][t(p)], one fp32 add, rounded to T
+template <typename T>
+__device__ __forceinline__ float pair_ld(const T* p);
+template <>
+__device__ __forceinline__ float pair_ld<float>(const float* p) { return *p; }
+template <>
+__device__ __forceinline__ float pair_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <>
+__device__ __forceinline__ float pair_ld<__half>(const __half* p) { return __half2float(*p); }
+template <typename T>
+__device__ __forceinline__ void pair_st(T* p, float v);
+template <>
+__device__ __forceinline__ void pair_st<float>(float* p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void pair_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ void pair_st<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) cross_merge2d_pair_kernel(const T* __restrict__ g, T* __restrict__ dx, long planes,
+                                                                 int dim, long H, long W, int tiles_w, int tiles_h) {
+  __shared__ float t1[kCT][kCT + 1];
+  const long L = H * W;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long blk = blockIdx.x;; blk += gridDim.x) {
+    const long plane = blk / ((long)tiles_w * tiles_h);
+    const int tr = (int)(blk % ((long)tiles_w * tiles_h));
+    if (plane >= planes) break;
+    const long h0 = (long)(tr / tiles_w) * kCT, w0 = (long)(tr % tiles_w) * kCT;
+    const long b = plane / dim;
+    const int dd = (int)(plane % dim);
+    const T* i0 = g + ((b * 2 + 0) * dim + dd) * L;
+    const T* i1 = g + ((b * 2 + 1) * dim + dd) * L;
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {
+      const long w = w0 + ty + r, h = h0 + tx;
+      if (h < H && w < W) t1[ty + r][tx] = pair_ld<T>(i1 + w * H + h);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kCT; r += 8) {
+      const long h = h0 + ty + r, w = w0 + tx;
+      if (h < H && w < W) {
+        const long p = h * W + w;
+        pair_st<T>(dx + plane * L + p, pair_ld<T>(i0 + p) + t1[tx][ty + r]);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 static int tiled_grid(long planes, long H, long W, int* tw, int* th) {
   *tw = (int)((W + kCT - 1) / kCT), *th = (int)((H + kCT - 1) / kCT);
   const long blocks = planes * *tw * *th, cap = 148L * 32;
@@ -332,6 +423,48 @@ int nz_cross_merge_bwd(const float* dy, float* d_out_y, int32_t batch, int32_t d
   const int threads = nz::launch_cfg(rows * 2 * nspatial * s.L, &grid);
   nz::cross_merge_bwd_kernel<<<grid, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(dy, d_out_y, rows, dim, s,
                                                                                           mode);
+  nz::count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+}
+
+
+int nz_cross_scan_pair(const void* x, void* xs2, int32_t dtype, int32_t batch, int32_t dim, int32_t H, int32_t W,
+                       void* stream) {
+  if (!x || !xs2 || batch < 1 || dim < 1 || H < 1 || W < 1) return NZ_EINVAL;
+  const long rows = (long)batch * dim;
+  int tw, th;
+  const int g = nz::tiled_grid(rows, H, W, &tw, &th);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == NZ_F32)
+    nz::cross_scan2d_pair_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(x), static_cast<uint32_t*>(xs2),
+                                                              rows, dim, H, W, tw, th);
+  else if (dtype == NZ_BF16 || dtype == NZ_F16)
+    nz::cross_scan2d_pair_kernel<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<uint16_t*>(xs2),
+                                                              rows, dim, H, W, tw, th);
+  else
+    return NZ_EINVAL;
+  nz::count_launch(1);
+  return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+}
+
+int nz_cross_merge_pair(const void* dxs2, void* dx, int32_t dtype, int32_t batch, int32_t dim, int32_t H, int32_t W,
+                        void* stream) {
+  if (!dxs2 || !dx || batch < 1 || dim < 1 || H < 1 || W < 1) return NZ_EINVAL;
+  const long rows = (long)batch * dim;
+  int tw, th;
+  const int g = nz::tiled_grid(rows, H, W, &tw, &th);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == NZ_F32)
+    nz::cross_merge2d_pair_kernel<float><<<g, 256, 0, st>>>(static_cast<const float*>(dxs2), static_cast<float*>(dx), rows,
+                                                            dim, H, W, tw, th);
+  else if (dtype == NZ_BF16)
+    nz::cross_merge2d_pair_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(dxs2),
+                                                                    static_cast<__nv_bfloat16*>(dx), rows, dim, H, W, tw, th);
+  else if (dtype == NZ_F16)
+    nz::cross_merge2d_pair_kernel<__half><<<g, 256, 0, st>>>(static_cast<const __half*>(dxs2), static_cast<__half*>(dx),
+                                                             rows, dim, H, W, tw, th);
+  else
+    return NZ_EINVAL;
   nz::count_launch(1);
   return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
 }

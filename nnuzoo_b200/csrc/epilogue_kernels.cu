@@ -112,6 +112,8 @@ struct EpArgs {
   float *dgamma, *dbeta;
   int B, D, H, W, TH, TW;  // TH, TW powers of two, TH * TW * D = 8192
   int lTH, lTW;            // their log2
+  int folded;              // 1: out_y / d_out_y hold the four directions UN-flipped, ordered {row-major forward, row-major
+                           // backward, column-major forward, column-major backward} as the scan's rev_mask path writes them
   float eps;
 };
 
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kEpThreads, 4) ss2d_epilogue_fwd_kernel(EpArgs
       if (h < a.H && w < a.W) {
         const long pos = (long)h * a.W + w;
         v = oy[d * L + pos];
-        v = v + oy[2 * ks + d * L + (L - 1 - pos)];
+        v = v + (a.folded ? oy[ks + d * L + pos] : oy[2 * ks + d * L + (L - 1 - pos)]);
       }
       sm[d * S + (p >> a.lTW) * TW1 + (p & (a.TW - 1))] = v;
     }
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(kEpThreads, 4) ss2d_epilogue_fwd_kernel(EpArgs
       const int h = tl.h0 + qh, w = tl.w0 + qw;
       if (h < a.H && w < a.W) {
         const long j = (long)w * a.H + h;
-        const float v1 = oy[ks + d * L + j], v3 = oy[3 * ks + d * L + (L - 1 - j)];
+        const float v1 = a.folded ? oy[2 * ks + d * L + j] : oy[ks + d * L + j];
+        const float v3 = oy[3 * ks + d * L + (a.folded ? j : L - 1 - j)];
         float* s = sm + d * S + qh * TW1 + qw;
         *s = (*s + v1) + v3;
       }
@@ -296,7 +299,10 @@ __global__ void __launch_bounds__(kEpThreads, 3) ss2d_epilogue_bwd_kernel(EpArgs
         const long pos = (long)h * a.W + w;
         const float v = sm[d * S + (p >> a.lTW) * TW1 + (p & (a.TW - 1))];
         e_st<TG>(go + d * L + pos, v);
-        e_st<TG>(go + 2 * ks + d * L + (L - 1 - pos), v);
+        if (a.folded)
+          e_st<TG>(go + ks + d * L + pos, v);
+        else
+          e_st<TG>(go + 2 * ks + d * L + (L - 1 - pos), v);
       }
     }
 #pragma unroll 8
@@ -307,8 +313,8 @@ __global__ void __launch_bounds__(kEpThreads, 3) ss2d_epilogue_bwd_kernel(EpArgs
       if (h < a.H && w < a.W) {
         const long j = (long)w * a.H + h;
         const float v = sm[d * S + qh * TW1 + qw];
-        e_st<TG>(go + ks + d * L + j, v);
-        e_st<TG>(go + 3 * ks + d * L + (L - 1 - j), v);
+        e_st<TG>(go + (a.folded ? 2 : 1) * ks + d * L + j, v);
+        e_st<TG>(go + 3 * ks + d * L + (a.folded ? j : L - 1 - j), v);
       }
     }
   }
@@ -347,10 +353,9 @@ static bool ep_config(EpArgs& a, size_t* smem, int* grid, bool bwd) {
 
 extern "C" int nz_ss2d_epilogue_supported(int32_t D) { return nz::ep_supported(D) ? 1 : 0; }
 
-extern "C" int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma,
-                                    const float* beta, void* out, float* y_merged, float* mean, float* rstd,
-                                    int32_t z_dtype, int32_t out_dtype, int32_t batch, int32_t D, int32_t H, int32_t W,
-                                    float eps, void* stream) {
+static int ep_fwd_impl(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma, const float* beta,
+                       void* out, float* y_merged, float* mean, float* rstd, int32_t z_dtype, int32_t out_dtype,
+                       int32_t batch, int32_t D, int32_t H, int32_t W, float eps, void* stream, int folded) {
   using namespace nz;
   if (!out_y || !z || !z_stride || !out || !y_merged || !mean || !rstd || batch < 1 || H < 1 || W < 1) {
     set_error("nz_ss2d_epilogue_fwd: null pointer or empty shape");
@@ -359,6 +364,7 @@ extern "C" int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int
   EpArgs a{};
   a.out_y = out_y, a.z = z, a.z_bs = z_stride[0], a.z_ls = z_stride[1], a.gamma = gamma, a.beta = beta, a.out = out;
   a.ym = y_merged, a.mean = mean, a.rstd = rstd, a.B = batch, a.D = D, a.H = H, a.W = W, a.eps = eps;
+  a.folded = folded;
   size_t smem;
   int grid;
   if (!ep_config(a, &smem, &grid, false)) {
@@ -388,11 +394,10 @@ extern "C" int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int
   return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
 }
 
-extern "C" int nz_ss2d_epilogue_bwd(const void* dout, const float* y_merged, const float* mean, const float* rstd,
-                                    const void* z, const int64_t* z_stride, const float* gamma, const float* beta,
-                                    void* d_out_y, void* dz, float* dgamma, float* dbeta, int32_t z_dtype,
-                                    int32_t out_dtype, int32_t grad_dtype, int32_t batch, int32_t D, int32_t H, int32_t W,
-                                    void* stream) {
+static int ep_bwd_impl(const void* dout, const float* y_merged, const float* mean, const float* rstd, const void* z,
+                       const int64_t* z_stride, const float* gamma, const float* beta, void* d_out_y, void* dz,
+                       float* dgamma, float* dbeta, int32_t z_dtype, int32_t out_dtype, int32_t grad_dtype, int32_t batch,
+                       int32_t D, int32_t H, int32_t W, void* stream, int folded) {
   using namespace nz;
   if (!dout || !y_merged || !mean || !rstd || !z || !z_stride || !d_out_y || !dz || batch < 1 || H < 1 || W < 1) {
     set_error("nz_ss2d_epilogue_bwd: null pointer or empty shape");
@@ -402,6 +407,7 @@ extern "C" int nz_ss2d_epilogue_bwd(const void* dout, const float* y_merged, con
   a.dout = dout, a.ym = const_cast<float*>(y_merged), a.mean = const_cast<float*>(mean), a.rstd = const_cast<float*>(rstd);
   a.z = z, a.z_bs = z_stride[0], a.z_ls = z_stride[1], a.gamma = gamma, a.beta = beta, a.d_out_y = d_out_y, a.dz = dz;
   a.dgamma = dgamma, a.dbeta = dbeta, a.B = batch, a.D = D, a.H = H, a.W = W;
+  a.folded = folded;
   size_t smem;
   int grid;
   if (!ep_config(a, &smem, &grid, true)) {
@@ -433,4 +439,37 @@ extern "C" int nz_ss2d_epilogue_bwd(const void* dout, const float* y_merged, con
 #undef NZ_EP_BWD
   count_launch(1);
   return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
+}
+
+extern "C" int nz_ss2d_epilogue_fwd(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma,
+                                    const float* beta, void* out, float* y_merged, float* mean, float* rstd,
+                                    int32_t z_dtype, int32_t out_dtype, int32_t batch, int32_t D, int32_t H, int32_t W,
+                                    float eps, void* stream) {
+  return ep_fwd_impl(out_y, z, z_stride, gamma, beta, out, y_merged, mean, rstd, z_dtype, out_dtype, batch, D, H, W, eps,
+                     stream, 0);
+}
+extern "C" int nz_ss2d_epilogue_bwd(const void* dout, const float* y_merged, const float* mean, const float* rstd,
+                                    const void* z, const int64_t* z_stride, const float* gamma, const float* beta,
+                                    void* d_out_y, void* dz, float* dgamma, float* dbeta, int32_t z_dtype,
+                                    int32_t out_dtype, int32_t grad_dtype, int32_t batch, int32_t D, int32_t H, int32_t W,
+                                    void* stream) {
+  return ep_bwd_impl(dout, y_merged, mean, rstd, z, z_stride, gamma, beta, d_out_y, dz, dgamma, dbeta, z_dtype, out_dtype,
+                     grad_dtype, batch, D, H, W, stream, 0);
+}
+// Same kernels on the folded direction layout (nz_scan_fwd / nz_scan_bwd with rev_mask = 0b1010, u_gdiv = 2):
+// out_y / d_out_y = (batch, {row-major fwd, row-major bwd, column-major fwd, column-major bwd}, D, L), nothing flipped.
+extern "C" int nz_ss2d_epilogue_fwd_folded(const float* out_y, const void* z, const int64_t* z_stride, const float* gamma,
+                                           const float* beta, void* out, float* y_merged, float* mean, float* rstd,
+                                           int32_t z_dtype, int32_t out_dtype, int32_t batch, int32_t D, int32_t H,
+                                           int32_t W, float eps, void* stream) {
+  return ep_fwd_impl(out_y, z, z_stride, gamma, beta, out, y_merged, mean, rstd, z_dtype, out_dtype, batch, D, H, W, eps,
+                     stream, 1);
+}
+extern "C" int nz_ss2d_epilogue_bwd_folded(const void* dout, const float* y_merged, const float* mean, const float* rstd,
+                                           const void* z, const int64_t* z_stride, const float* gamma, const float* beta,
+                                           void* d_out_y, void* dz, float* dgamma, float* dbeta, int32_t z_dtype,
+                                           int32_t out_dtype, int32_t grad_dtype, int32_t batch, int32_t D, int32_t H,
+                                           int32_t W, void* stream) {
+  return ep_bwd_impl(dout, y_merged, mean, rstd, z, z_stride, gamma, beta, d_out_y, dz, dgamma, dbeta, z_dtype, out_dtype,
+                     grad_dtype, batch, D, H, W, stream, 1);
 }

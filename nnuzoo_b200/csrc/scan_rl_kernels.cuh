@@ -29,6 +29,8 @@
 #include "nz_common.cuh"
 #include "scan_kernels.cuh"  // packed fp32x2 helpers, lds/sts helpers
 
+#include <type_traits>
+
 namespace nz {
 
 constexpr int kFine = NZ_FINE;  // steps per block = fine checkpoint interval
@@ -61,6 +63,11 @@ struct alignas(64) RlArgs {
   int single;    // one warp owns each dB / dC element (dpg == 32): plain stores instead of RED
   unsigned zero; // always 0 (see order_after)
   int v2;        // backward main pass: 1 = butterfly version (scan_bwd_rl2_kernel), 0 = slab version
+  int rev_mask;  // bit g set: the rows of group g walk the sequence BACKWARDS (kRevCap kernels only): the forward
+                 // recurrence runs from t = L-1 down to 0 over the same, un-flipped arrays -- SS2D's flipped
+                 // directions without a flipped copy (m2net.py:176)
+  int u_gdiv;    // u has dim / u_gdiv rows per batch entry: group g reads the rows of group g / u_gdiv (the two
+                 // directions that walk the same array forwards and backwards share it); 1 = plain
   int wide;      // every fp32 output row / checkpoint run is 32-byte aligned: one 32-byte store per block
   int v2f;       // forward main pass: 1 = pipelined version (scan_fwd_rl2_kernel)
 };
@@ -190,7 +197,9 @@ __device__ __forceinline__ void lds_bc(uint32_t tile_s, int n, float (&v)[8]) {
 // ================================================================================================
 // kFwd = false: reverse recurrence R_{t-1} = a_t (C_t dy_t + R_t) over (delta, dout, [z], C);  chunks 1 .. nchunks-1
 // kFwd = true : forward recurrence h_t = a_t h_{t-1} + dl_t u_t B_t over (delta, u, B);        chunks 0 .. nchunks-2
-template <typename T, bool kHasZ, bool kFwd>
+// kRevCap: compiled with support for reversed groups (RlArgs::rev_mask) and shared u rows (RlArgs::u_gdiv); the plain
+// instantiation carries neither the branch nor the second copy of the state loop.
+template <typename T, bool kHasZ, bool kFwd, bool kRevCap = false>
 __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_constant__ RlArgs a) {
   using Cfg = RlCfg<T>;
   constexpr int TB = Cfg::TB, NBLK = Cfg::NBLK, ROWT = Cfg::ROWT, BCT = Cfg::BCT;
@@ -205,12 +214,15 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
   // work item: nobody needs the aggregate of the first (backward) / last (forward) chunk in time
   const int nc1 = a.nchunks - 1;
   const int item = blockIdx.x;
-  const int c = item % nc1 + (kFwd ? 0 : 1);
   int w = item / nc1;
   const int rb = w % a.nrb;
   w /= a.nrb;
   const int g = w % a.ngroups, b = w / a.ngroups;
+  const bool rev = kRevCap && ((a.rev_mask >> g) & 1);
+  const bool down = kFwd ? rev : !rev;  // walking direction along the sequence
+  const int c = item % nc1 + (down ? 1 : 0);  // the last chunk in walking order needs no aggregate
   const int d0 = g * a.dpg + rb * 32, d = d0 + lane;
+  const int r1 = (kRevCap && kFwd) ? (g / a.u_gdiv) * a.dpg + rb * 32 : d0;  // rows of g_row1 (u when kFwd)
   const long rowg = (long)b * a.dim + d;
   const int t_lo = c * a.tpc, t_hi = min(a.ntl, t_lo + a.tpc);
 
@@ -218,12 +230,12 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
     uint8_t* st = smem + s * STAGE;
     mbar_arrive_expect_tx(&bars[s], STAGE);
     tma_load_4d(st, &a.g_delta, &bars[s], 0, t, d0, b);
-    tma_load_4d(st + ROWT, &a.g_row1, &bars[s], 0, t, d0, b);
+    tma_load_4d(st + ROWT, &a.g_row1, &bars[s], 0, t, r1, b);
     if (kHasZ) tma_load_4d(st + 2 * ROWT, &a.g_z, &bars[s], 0, t, d0, b);
     tma_load_5d(st + NROW * ROWT, &a.g_bc, &bars[s], 0, t, 0, g, b);
   };
   const int nt = t_hi - t_lo;
-  auto tile_of = [&](int k) { return kFwd ? t_lo + k : t_hi - 1 - k; };  // k-th tile in walking order
+  auto tile_of = [&](int k) { return down ? t_hi - 1 - k : t_lo + k; };  // k-th tile in walking order
   if (lane == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
     const uint32_t st = smem_s + s * STAGE;
 #pragma unroll 1
     for (int bi = 0; bi < NBLK; ++bi) {
-      const int blk = kFwd ? bi : NBLK - 1 - bi;
+      const int blk = down ? NBLK - 1 - bi : bi;
       float dl[8], dy[8];  // dy: dout (backward) / u (forward)
       lds_block<T>(st, lane, blk, dl);
       lds_block<T>(st + ROWT, lane, blk, dy);
@@ -270,26 +282,39 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
         if (kFwd) dy[i] *= x;  // dl_t u_t
         dl[i] = NZ_RL_POLY_AGG > 0 ? fminf(fmaxf(x, -dlim), dlim) : x;
       }
+      auto states = [&](auto down_tag) {
+        constexpr bool kDown = decltype(down_tag)::value;
 #pragma unroll
-      for (int n = 0; n < kMaxState; ++n) {
-        float cv[8];
-        lds_block<T>(st + NROW * ROWT, n, blk, cv);
-        float av[8];
+        for (int n = 0; n < kMaxState; ++n) {
+          float cv[8];
+          lds_block<T>(st + NROW * ROWT, n, blk, cv);
+          float av[8];
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const float2 e2 = ex2_pair(rl_poly_state(n, NZ_RL_POLY_AGG), mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n])));
-          av[2 * kk] = e2.x;
-          av[2 * kk + 1] = e2.y;
+          for (int kk = 0; kk < 4; ++kk) {
+            const float2 e2 =
+                ex2_pair(rl_poly_state(n, NZ_RL_POLY_AGG), mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n])));
+            av[2 * kk] = e2.x;
+            av[2 * kk + 1] = e2.y;
+          }
+          float r = R[n];
+#pragma unroll
+          for (int ii = 0; ii < 8; ++ii) {
+            const int i = kDown ? 7 - ii : ii;
+            if constexpr (kFwd)
+              r = fmaf(av[i], r, cv[i] * dy[i]);  // h_t = a_t h_{t-1} + b_t
+            else
+              r = av[i] * fmaf(cv[i], dy[i], r);  // R_{t-1} = a_t (C_t dy_t + R_t)
+          }
+          R[n] = r;
         }
-        float r = R[n];
-        if constexpr (kFwd) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) r = fmaf(av[i], r, cv[i] * dy[i]);  // h_t = a_t h_{t-1} + b_t
-        } else {
-#pragma unroll
-          for (int i = 7; i >= 0; --i) r = av[i] * fmaf(cv[i], dy[i], r);  // R_{t-1} = a_t (C_t dy_t + R_t)
-        }
-        R[n] = r;
+      };
+      if constexpr (kRevCap) {
+        if (down)
+          states(std::true_type{});
+        else
+          states(std::false_type{});
+      } else {
+        states(std::integral_constant<bool, !kFwd>{});
       }
     }
     __syncwarp();  // every lane is done with stage s
@@ -309,11 +334,12 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
 // to last for the forward (h)
 static __global__ void __launch_bounds__(128) scan_rl_combine_kernel(const float* __restrict__ G, const float* __restrict__ Q,
                                                                     float* __restrict__ Rin, long nrows, int nchunks,
-                                                                    int fwd) {
+                                                                    int fwd, int dim, int dpg, int rev_mask) {
   const long i = blockIdx.x * 128L + threadIdx.x;
   if (i >= nrows * kMaxState) return;
   const long row = i / kMaxState;
   const int n = (int)(i % kMaxState);
+  fwd ^= (rev_mask >> ((int)(row % dim) / dpg)) & 1;  // reversed groups walk the chunks the other way
   const long base = row * nchunks * kMaxState + n;
   float r = 0.f;
   if (fwd) {
@@ -716,7 +742,7 @@ __device__ __forceinline__ void lds_bc2(uint32_t base, int q, float (&v)[8]) {
 #else
 #define NZ_RL_BWD2_BOUNDS __launch_bounds__(32, NZ_RL_BWD2_MINB)
 #endif
-template <typename T, bool kHasZ, bool kSingle>
+template <typename T, bool kHasZ, bool kSingle, bool kRevCap = false>
 __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ RlArgs a) {
   using Cfg = RlCfg<T>;
   using SM = RlMain2Smem<T, kHasZ>;
@@ -741,15 +767,20 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
   const long rowg = (long)b * a.dim + d;
   const int t_lo = c * a.tpc, t_hi = min(a.ntl, t_lo + a.tpc);
   const int j_lo = t_lo * NBLK, j_hi = t_hi * NBLK;  // fine blocks [j_lo, j_hi), walked last to first
+  const bool rev = kRevCap && ((a.rev_mask >> g) & 1);              // the forward walked this group backwards
+  const int ur = kRevCap ? (g / a.u_gdiv) * a.dpg + rb * 32 : d0;   // rows of u
+  const int nblk = j_hi - j_lo;
+  auto jof = [&](int k) { return rev ? j_lo + k : j_hi - 1 - k; };  // k-th block in walking order
+  const int jprev = rev ? 1 : -1;  // the block whose end state enters block j lies at j + jprev
 
   auto issue_rows = [&](int j, int s) {
     uint8_t* st = smem + s * SM::RSTAGE;
     mbar_arrive_expect_tx(&bars[s], ROWS_TX);
-    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, d0, b);
+    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, ur, b);
     tma_load_4d(st + RB, &a.tm_delta, &bars[s], 0, j, d0, b);
     tma_load_4d(st + 2 * RB, &a.tm_dout, &bars[s], 0, j, d0, b);
     if (kHasZ) tma_load_4d(st + 3 * RB, &a.tm_z, &bars[s], 0, j, d0, b);
-    tma_load_4d(st + SM::OFF_XF, &a.tm_xf, &bars[s], 0, j - 1, d0, b);  // block -1 is out of bounds: zero fill
+    tma_load_4d(st + SM::OFF_XF, &a.tm_xf, &bars[s], 0, j + jprev, d0, b);  // out of bounds (first block): zero fill
   };
   auto issue_bc = [&](int j, int s) {
     uint8_t* st = smem + SM::OFF_BC + s * SM::BSTAGE;
@@ -761,11 +792,11 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-    issue_rows(j_hi - 1, 0);
-    issue_bc(j_hi - 1, 0);
-    if (j_hi - 2 >= j_lo) {
-      issue_rows(j_hi - 2, 1);
-      issue_bc(j_hi - 2, 1);
+    issue_rows(jof(0), 0);
+    issue_bc(jof(0), 0);
+    if (nblk > 1) {
+      issue_rows(jof(1), 1);
+      issue_bc(jof(1), 1);
     }
   }
   __syncwarp();
@@ -799,9 +830,9 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
   long Lq = a.L * 16;  // byte pitch of four state rows of dB / dC
   asm volatile("" : "+l"(Lq));
 
-  int k = 0;
 #pragma unroll 1
-  for (int jb = j_hi - 1; jb >= j_lo; --jb, ++k) {
+  for (int k = 0; k < nblk; ++k) {
+    const int jb = jof(k);
     const int s = k & 1;
     const uint32_t ph = (uint32_t)(k >> 1) & 1u;
     mbar_wait(&bars[s], ph);
@@ -844,7 +875,7 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
     }
     // this stage's row data now lives in registers: request the block after the next one into it
     __syncwarp();
-    if (lane == 0 && jb - 2 >= j_lo) issue_rows(jb - 2, s);
+    if (lane == 0 && k + 2 < nblk) issue_rows(jof(k + 2), s);
     mbar_wait(&bars[2 + s], ph);
     const uint32_t tB = bc_s + s * SM::BSTAGE;
     uint32_t tbj[4];
@@ -856,6 +887,8 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
     lds_bc2<T>(tbj[0], 0, bcv[0][0]);
     lds_bc2<T>(tbj[0] + BB, 0, bcv[0][1]);
     float2 K0[8], K1[8];  // [0..3] dB, [4..7] dC of a slot pair, as time pairs
+    auto states = [&](auto rev_tag) {
+    constexpr bool kR = decltype(rev_tag)::value;
 #pragma unroll
     for (int n = 0; n < kMaxState; ++n) {  // n = code slot; the state is n ^ m
       float (&bv)[8] = bcv[n & 1][0];
@@ -884,22 +917,25 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
         cdy[2 * kk + 1] = c2.y;
       }
       // forward recurrence for h, reverse recurrence for dh (independent chains)
+      // (a reversed group -- kR -- walked the block from step 7 down to 0, so both chains run the other way)
       float bsave[8];
       float h = hp[n];
-      float dh = cdy[7] + R[n];
-      dd[7] = dh;
+      float dh = cdy[kR ? 0 : 7] + R[n];
+      dd[kR ? 0 : 7] = dh;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = kR ? 7 - ii : ii;
         bsave[i] = hh[i];
         h = fmaf(av[i], h, hh[i]);
         hh[i] = h;
-        if (i < 7) {
-          const int j = 6 - i;
-          dh = fmaf(av[j + 1], dh, cdy[j]);
+        if (ii < 7) {
+          const int j = kR ? ii + 1 : 6 - ii;          // step whose dh is next
+          const int jn = kR ? ii : 7 - ii;             // the step after it in walking order
+          dh = fmaf(av[jn], dh, cdy[j]);
           dd[j] = dh;
         }
       }
-      R[n] = av[0] * dd[0];  // R leaving the block
+      R[n] = av[kR ? 7 : 0] * dd[kR ? 7 : 0];  // R leaving the block
       // element-wise products, packed over time pairs
       float2 gs2 = f2(0.f, 0.f);
       float2 V[8];  // this slot's dB (0..3) and dC (4..7) products
@@ -956,8 +992,17 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
         dGq += Lq;
       }
     }
+    };
+    if constexpr (kRevCap) {
+      if (rev)
+        states(std::true_type{});
+      else
+        states(std::false_type{});
+    } else {
+      states(std::false_type{});
+    }
     __syncwarp();  // every lane is done with B/C stage s
-    if (lane == 0 && jb - 2 >= j_lo) issue_bc(jb - 2, s);
+    if (lane == 0 && k + 2 < nblk) issue_bc(jof(k + 2), s);
 
     // ---- per-(row, t) epilogue of the block ----
     const long tpos = (long)jb * kFine;
@@ -1009,7 +1054,7 @@ struct RlFwdSmem {
 #ifndef NZ_RL_FWD_MINB
 #define NZ_RL_FWD_MINB 16
 #endif
-template <typename T, bool kHasZ>
+template <typename T, bool kHasZ, bool kRevCap = false>
 __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const __grid_constant__ RlArgs a) {
   using SM = RlFwdSmem<T, kHasZ>;
   constexpr int NBLK = RlCfg<T>::NBLK, RB = SM::RB, BB = SM::BB;
@@ -1031,11 +1076,15 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
   const int t_lo = c * a.tpc, t_hi = min(a.ntl, t_lo + a.tpc);
   const int j_lo = t_lo * NBLK, j_hi = t_hi * NBLK;
   const long nbt = a.L / kFine;
+  const bool rev = kRevCap && ((a.rev_mask >> g) & 1);              // this group walks the sequence backwards
+  const int ur = kRevCap ? (g / a.u_gdiv) * a.dpg + rb * 32 : d0;   // rows of u
+  const int nblk = j_hi - j_lo;
+  auto jof = [&](int k) { return rev ? j_hi - 1 - k : j_lo + k; };  // k-th block in walking order
 
   auto issue = [&](int j, int s) {
     uint8_t* st = smem + s * SM::RSTAGE;
     mbar_arrive_expect_tx(&bars[s], SM::NROWT * RB);
-    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, d0, b);
+    tma_load_4d(st, &a.tm_u, &bars[s], 0, j, ur, b);
     tma_load_4d(st + RB, &a.tm_delta, &bars[s], 0, j, d0, b);
     if (kHasZ) tma_load_4d(st + 2 * RB, &a.tm_z, &bars[s], 0, j, d0, b);
     uint8_t* sb = smem + SM::OFF_BC + s * SM::BSTAGE;
@@ -1047,8 +1096,8 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-    issue(j_lo, 0);
-    if (j_lo + 1 < j_hi) issue(j_lo + 1, 1);
+    issue(jof(0), 0);
+    if (nblk > 1) issue(jof(1), 1);
   }
   __syncwarp();
   float A2[kMaxState], h[kMaxState];
@@ -1068,9 +1117,9 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
   for (int n = 0; n < kMaxState; ++n) amax = fmaxf(amax, fabsf(A2[n]));
   const float dlim = 126.f / fmaxf(amax, 1e-30f);  // |A2 * dl| <= 126 for the exponent arithmetic of ex2_poly2
 
-  int k = 0;
 #pragma unroll 1
-  for (int jb = j_lo; jb < j_hi; ++jb, ++k) {
+  for (int k = 0; k < nblk; ++k) {
+    const int jb = jof(k);
     const int s = k & 1;
     const uint32_t ph = (uint32_t)(k >> 1) & 1u;
     mbar_wait(&bars[s], ph);
@@ -1090,33 +1139,53 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
     }
     mbar_wait(&bars[2 + s], ph);
     const uint32_t tB = smem_s + SM::OFF_BC + s * SM::BSTAGE, tC = tB + BB;
+    auto states = [&](auto rev_tag) {
+      constexpr bool kR = decltype(rev_tag)::value;
 #pragma unroll
-    for (int n = 0; n < kMaxState; ++n) {
-      float bv[8], cv[8], hh[8];
-      lds_bc<T>(tB, n, bv);
-      lds_bc<T>(tC, n, cv);
-      float hc = h[n];
+      for (int n = 0; n < kMaxState; ++n) {
+        float bv[8], cv[8], hh[8];
+        lds_bc<T>(tB, n, bv);
+        lds_bc<T>(tC, n, cv);
+        float hc = h[n];
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float2 e2 = ex2_pair(rl_poly_state(n, NZ_RL_POLY_FWD), mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n])));
-        const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
-        hc = fmaf(e2.x, hc, b2.x);
-        hh[2 * kk] = hc;
-        hc = fmaf(e2.y, hc, b2.y);
-        hh[2 * kk + 1] = hc;
+        for (int q = 0; q < 4; ++q) {
+          const int kk = kR ? 3 - q : q;
+          const float2 e2 =
+              ex2_pair(rl_poly_state(n, NZ_RL_POLY_FWD), mul2(f2(dl[2 * kk], dl[2 * kk + 1]), f2(A2[n], A2[n])));
+          const float2 b2 = mul2(f2(dlu[2 * kk], dlu[2 * kk + 1]), f2(bv[2 * kk], bv[2 * kk + 1]));
+          if constexpr (kR) {
+            hc = fmaf(e2.y, hc, b2.y);
+            hh[2 * kk + 1] = hc;
+            hc = fmaf(e2.x, hc, b2.x);
+            hh[2 * kk] = hc;
+          } else {
+            hc = fmaf(e2.x, hc, b2.x);
+            hh[2 * kk] = hc;
+            hc = fmaf(e2.y, hc, b2.y);
+            hh[2 * kk + 1] = hc;
+          }
+        }
+        h[n] = hc;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          float2 y2 = f2(y[2 * kk], y[2 * kk + 1]);
+          y2 = fma2(f2(cv[2 * kk], cv[2 * kk + 1]), f2(hh[2 * kk], hh[2 * kk + 1]), y2);
+          y[2 * kk] = y2.x;
+          y[2 * kk + 1] = y2.y;
+        }
       }
-      h[n] = hc;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        float2 y2 = f2(y[2 * kk], y[2 * kk + 1]);
-        y2 = fma2(f2(cv[2 * kk], cv[2 * kk + 1]), f2(hh[2 * kk], hh[2 * kk + 1]), y2);
-        y[2 * kk] = y2.x;
-        y[2 * kk + 1] = y2.y;
-      }
+    };
+    if constexpr (kRevCap) {
+      if (rev)
+        states(std::true_type{});
+      else
+        states(std::false_type{});
+    } else {
+      states(std::false_type{});
     }
     // every lane is done with this block's stages: request the block after the next one
     __syncwarp();
-    if (lane == 0 && jb + 2 < j_hi) issue(jb + 2, s);
+    if (lane == 0 && k + 2 < nblk) issue(jof(k + 2), s);
     if constexpr (kHasZ) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] *= zz[i] * sigmoid_f(zz[i]);
@@ -1138,7 +1207,8 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
           reinterpret_cast<float4*>(xo)[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
       }
     }
-    if ((jb + 1) % BPC == 0 || jb + 1 == nbt) {
+    // coarse checkpoints: h after the last block of every 128-step chunk in walking order
+    if (rev ? jb % BPC == 0 : ((jb + 1) % BPC == 0 || jb + 1 == nbt)) {
       float4* xo = reinterpret_cast<float4*>(a.x + (rowg * a.nck + jb / BPC) * kMaxState);
 #pragma unroll
       for (int q = 0; q < 4; ++q) xo[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);

@@ -101,6 +101,84 @@ class SS2DCoreFn(torch.autograd.Function):
                 dg.to(gdt) if dg is not None else None, db.to(bdt) if db is not None else None, None, None, None, None)
 
 
+# direction order of the folded layout: k' = 2 * (array: 0 row-major, 1 column-major) + (0 forwards, 1 backwards); in the
+# reference's numbering (m2net.py:175-177: k0 row-major, k1 column-major, k2 / k3 their flips) that is k = (0, 2, 1, 3)
+FOLD_PERM = (0, 2, 1, 3)
+_FOLD_REV_MASK = 0b1010
+_FOLD_U_GDIV = 2
+
+
+class SS2DFoldedFn(torch.autograd.Function):
+    """SS2DCoreFn without the flipped copies: the scan reads xs2 (B, 2, D, L) = {x row-major, x column-major}, directions
+    k' = 1, 3 walk them from t = L - 1 down to 0 (``rev_mask``), out_y' / d_out_y' (B, 4, D, L) stay un-flipped and the
+    epilogue kernels merge / scatter them without index reversal.  dts / Bs / Cs / As / Ds / dt_bias arrive in the folded
+    direction order (FOLD_PERM), computed from the un-flipped xs2."""
+
+    @staticmethod
+    def forward(ctx, xs2, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype):
+        bsz, two, D, L = xs2.shape
+        K = 4
+        if two != 2 or H * W != L or dts.shape != (bsz, K, D, L):
+            raise ValueError("ss2d_core_folded: xs2 must be (B, 2, D, H*W) and dts (B, 4, D, H*W)")
+        if z.shape != (bsz, H, W, D) or z.stride(3) != 1 or z.stride(1) != W * z.stride(2) or z.dtype not in _DT:
+            raise ValueError("ss2d_core_folded: z must be a (B, H, W, D) tensor with unit channel stride and collapsible H, W")
+        inner = _InnerCtx(any(ctx.needs_input_grad[:8]))
+        inner.needs_input_grad = inner.needs_input_grad + (False, False)
+        scan_out = torch.float32 if xs2.dtype != torch.float32 else None
+        out_y = SelectiveScanFn.forward(inner, xs2.view(bsz, 2 * D, L), dts.view(bsz, K * D, L), As, Bs, Cs, Ds, None,
+                                        dt_bias, True, False, scan_out, _FOLD_REV_MASK, _FOLD_U_GDIV)
+        dev = xs2.device
+        out = torch.empty((bsz, H, W, D), dtype=out_dtype, device=dev)
+        ym = torch.empty((bsz, L, D), dtype=torch.float32, device=dev)
+        mean = torch.empty(bsz * L, dtype=torch.float32, device=dev)
+        rstd = torch.empty_like(mean)
+        g32 = gamma.float().contiguous() if gamma is not None else None
+        b32 = beta.float().contiguous() if beta is not None else None
+        zs = (ctypes.c_int64 * 2)(z.stride(0), z.stride(2))
+        _native.bind_device(dev.index)
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(_native.lib().nz_ss2d_epilogue_fwd_folded(
+            _vp(out_y), _vp(z), zs, _vp(g32), _vp(b32), _vp(out), _vp(ym), _vp(mean), _vp(rstd), _DT[z.dtype],
+            _DT[out_dtype], bsz, D, H, W, float(eps), st), "nz_ss2d_epilogue_fwd_folded")
+        ctx.inner = inner
+        ctx.save_for_backward(ym, mean, rstd, z, g32, b32)
+        ctx.dims = (bsz, K, D, H, W)
+        ctx.dtypes = (xs2.dtype, out_dtype, gamma.dtype if gamma is not None else None,
+                      beta.dtype if beta is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        ym, mean, rstd, z, g32, b32 = ctx.saved_tensors
+        bsz, K, D, H, W = ctx.dims
+        op_dtype, out_dtype, gdt, bdt = ctx.dtypes
+        L = H * W
+        dev = ym.device
+        dout = dout.contiguous()
+        if dout.dtype != out_dtype:
+            dout = dout.to(out_dtype)
+        d_out_y = torch.empty((bsz, K * D, L), dtype=op_dtype, device=dev)   # the scan's operand dtype, folded layout
+        dz = torch.empty((bsz, H, W, D), dtype=z.dtype, device=dev)
+        dg = torch.zeros(D, dtype=torch.float32, device=dev) if g32 is not None else None
+        db = torch.zeros(D, dtype=torch.float32, device=dev) if b32 is not None else None
+        zs = (ctypes.c_int64 * 2)(z.stride(0), z.stride(2))
+        _native.bind_device(dev.index)
+        st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(_native.lib().nz_ss2d_epilogue_bwd_folded(
+            _vp(dout), _vp(ym), _vp(mean), _vp(rstd), _vp(z), zs, _vp(g32), _vp(b32), _vp(d_out_y), _vp(dz), _vp(dg),
+            _vp(db), _DT[z.dtype], _DT[out_dtype], _DT[op_dtype], bsz, D, H, W, st), "nz_ss2d_epilogue_bwd_folded")
+        du, ddelta, dA, dB, dC, dD, _dz, dbias, *_ = SelectiveScanFn.backward(ctx.inner, d_out_y)
+        ctx.inner = None
+        # (du is already summed over the forward and the backward walker of each array: SelectiveScanFn.backward)
+        return (du.view(bsz, 2, D, L), ddelta.view(bsz, K, D, L), dA, dB, dC, dD, dbias, dz,
+                dg.to(gdt) if dg is not None else None, db.to(bdt) if db is not None else None, None, None, None, None)
+
+
+def ss2d_core_folded(xs2, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype):
+    """xs2 (B, 2, D, L), dts (B, 4, D, L) contiguous, Bs / Cs (B, 4, N, L) views, all in folded direction order."""
+    return SS2DFoldedFn.apply(xs2, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, int(H), int(W), float(eps), out_dtype)
+
+
 def ss2d_core(xs, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype):
     """xs, dts (B, 4, D, L) contiguous; Bs, Cs (B, 4, N, L) (strided views fine); z (B, H, W, D) -> (B, H, W, D)."""
     return SS2DCoreFn.apply(xs, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, int(H), int(W), float(eps), out_dtype)

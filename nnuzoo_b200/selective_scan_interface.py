@@ -41,16 +41,18 @@ def _check_inputs(u, delta, A, B, C, D, z, delta_bias):
     if B.dim() < 3 or C.dim() < 3:
         raise NotImplementedError("only input-dependent (variable) B and C are implemented "
                                   "(the only form nnUZoo uses)")
-    if u.dim() != 3 or delta.shape != u.shape:
+    if u.dim() != 3 or delta.dim() != 3 or (delta.shape[0], delta.shape[2]) != (u.shape[0], u.shape[2]):
         raise ValueError("u and delta must both be (batch, dim, L)")
-    if A.dim() != 2 or A.shape[0] != u.shape[1]:
+    if A.dim() != 2 or A.shape[0] != delta.shape[1]:
         raise ValueError("A must be (dim, dstate)")
     if A.shape[1] > _native.NZ_MAX_DSTATE:
         raise NotImplementedError(f"d_state {A.shape[1]} > {_native.NZ_MAX_DSTATE} is not implemented")
 
 
-def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, force_generic, forward=False, xf=None):
-    batch, dim, L = u.shape
+def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, force_generic, forward=False, xf=None,
+                 rev_mask=0, u_gdiv=1):
+    batch, dim, L = delta.shape
+    desc.rev_mask, desc.u_gdiv = int(rev_mask), int(u_gdiv)
     desc.batch, desc.dim, desc.dstate, desc.ngroups = batch, dim, A.shape[1], B.shape[1]
     desc.seqlen = L
     desc.dtype = _DTYPES[u.dtype]
@@ -72,8 +74,9 @@ def _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, forc
     nbytes = _native.workspace_bytes(batch, dim)
     if forward:
         nbytes = max(nbytes, int(_native.lib().nz_scan_workspace_bytes_cp(ctypes.byref(desc))))
-    if xf is not None:  # backward with fine checkpoints: room for the chunk aggregates of the row-per-lane kernels
-        desc.xf = _ptr(xf)
+    if xf is not None or rev_mask or u_gdiv > 1:  # row-per-lane kernels: room for their chunk aggregates
+        if xf is not None:
+            desc.xf = _ptr(xf)
         nbytes = max(nbytes, int(_native.lib().nz_scan_workspace_bytes_bwd(ctypes.byref(desc))))
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=u.device)
     desc.workspace, desc.workspace_bytes = _ptr(ws), nbytes
@@ -89,8 +92,15 @@ class SelectiveScanFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
-                return_last_state=False, out_dtype=None):
+                return_last_state=False, out_dtype=None, rev_mask=0, u_gdiv=1):
+        # rev_mask / u_gdiv (NzScanDesc, ABI v4) are the folded-SS2D extension used by nnuzoo_b200.fused: groups that walk
+        # the sequence backwards over un-flipped arrays, and u rows shared by u_gdiv consecutive groups
         _check_inputs(u, delta, A, B, C, D, z, delta_bias)
+        if u_gdiv > 1 and u.shape[1] * u_gdiv != delta.shape[1]:
+            raise ValueError("with u_gdiv = n, u must be (batch, dim / n, L)")
+        if u_gdiv <= 1 and u.shape != delta.shape:
+            raise ValueError("u and delta must both be (batch, dim, L)")
+        ctx.fold = (int(rev_mask), int(u_gdiv))
         out_f32 = out_dtype == torch.float32 and u.dtype != torch.float32
         if out_dtype is not None and out_dtype != u.dtype and not out_f32:
             raise TypeError("out_dtype must be u's dtype or torch.float32")
@@ -120,7 +130,7 @@ class SelectiveScanFn(torch.autograd.Function):
             B = B.unsqueeze(1)
         if ctx.squeeze_C:
             C = C.unsqueeze(1)
-        batch, dim, L = u.shape
+        batch, dim, L = delta.shape
         N = A.shape[1]
         if B.shape != (batch, B.shape[1], N, L) or C.shape != B.shape:
             raise ValueError(f"B/C must be (batch, groups, dstate, L); got {tuple(B.shape)} {tuple(C.shape)}")
@@ -133,7 +143,8 @@ class SelectiveScanFn(torch.autograd.Function):
         out = torch.empty((batch, dim, L), dtype=torch.float32 if out_f32 else u.dtype, device=u.device)
         x = torch.empty((batch, dim, nchunks, N), dtype=torch.float32, device=u.device)
         desc = NzScanDesc()
-        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC, forward=True)
+        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, delta_softplus, _FORCE_GENERIC, forward=True,
+                          rev_mask=rev_mask, u_gdiv=u_gdiv)
         # fine checkpoints (h every NZ_FINE steps) feed the row-per-lane backward; only taken when a gradient will be asked
         # for and the problem qualifies (nz_scan_fine_bytes() > 0)
         xf = None
@@ -167,7 +178,7 @@ class SelectiveScanFn(torch.autograd.Function):
         xf = ctx.saved_tensors[9] if ctx.has_xf else None
         if dout.stride(-1) != 1 or dout.dtype != u.dtype:  # :57-58
             dout = dout.to(u.dtype).contiguous()
-        batch, dim, L = u.shape
+        batch, dim, L = delta.shape
         N, G = A.shape[1], B.shape[1]
         dev = u.device
         lib = _native.lib()
@@ -179,7 +190,8 @@ class SelectiveScanFn(torch.autograd.Function):
         dD = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_D else None
         dbias = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_bias else None
         desc = NzScanDesc()
-        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC, xf=xf)
+        ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC, xf=xf,
+                          rev_mask=ctx.fold[0], u_gdiv=ctx.fold[1])
         # dB / dC are overwritten when every element has a single owner tile, accumulated into (atomics) otherwise:
         # the library says which
         mk = torch.empty if lib.nz_scan_bwd_overwrites_dbc(ctypes.byref(desc)) else torch.zeros
@@ -193,6 +205,9 @@ class SelectiveScanFn(torch.autograd.Function):
         with torch.cuda.device(dev):
             _native.check(lib.nz_scan_bwd(ctypes.byref(desc), _stream(dev)), "nz_scan_bwd")
         del ws
+        if ctx.fold[1] > 1:  # groups that share u rows: their input gradients add up
+            n = ctx.fold[1]
+            du = du.view(batch, G // n, n, dim // G, L).sum(dim=2).view(batch, dim // n, L)
         if ctx.squeeze_B:  # :67-68
             dB = dB.squeeze(1)
         if ctx.squeeze_C:
@@ -201,7 +216,7 @@ class SelectiveScanFn(torch.autograd.Function):
         t_delta, t_A, t_B, t_C, t_D, t_z, t_bias = ctx.in_dtypes
         cast = lambda g, t: g if g is None or g.dtype == t else g.to(t)  # noqa: E731
         return (du, cast(ddelta, t_delta), cast(dA, t_A), cast(dB, t_B), cast(dC, t_C), cast(dD, t_D),
-                cast(dz, t_z), cast(dbias, t_bias), None, None, None)  # order of :69-74
+                cast(dz, t_z), cast(dbias, t_bias), None, None, None, None, None)  # order of :69-74
 
 
 def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,

@@ -25,7 +25,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import fused
-from .cross_scan import cross_merge, cross_scan
+from .cross_scan import cross_merge, cross_scan, cross_scan_pair
 from .dwconv import dwconv3x3_silu
 from .norm import LayerNorm
 from .proj import grouped_proj
@@ -47,6 +47,7 @@ class _CrossScanSSM(nn.Module):
     """Parameters and forward_core shared by SS2D (K = 4) and SSND (K = 4 or 6)."""
 
     fuse_epilogue = True   # SS2D: run scan -> merge -> out_norm -> gate as one autograd node (nnuzoo_b200.fused)
+    fold_directions = True  # ... on the folded direction layout: no flipped copies, the scan walks backwards instead
 
     def _init_ssm(self, d_model, d_state, expand, dt_rank, dt_min, dt_max, dt_init, dt_scale, dt_init_floor,
                   bias, dropout, k, factory_kwargs):
@@ -157,14 +158,41 @@ class _CrossScanSSM(nn.Module):
         if (not self.fuse_epilogue or self.k != 4 or x.dim() != 4 or not x.is_cuda
                 or self.selective_scan is not selective_scan_fn or not fused.supported(self.d_inner)):
             return None
+        H, W = x.shape[2:]
+        if z.stride(-1) != 1 or z.stride(1) != z.shape[2] * z.stride(2):
+            return None
+        if self.fold_directions and self.d_inner % 32 == 0 and (H * W * x.element_size()) % 128 == 0:
+            return self._folded_core(x, z)
         xs, dts, As, Bs, Cs = self._scan_operands(x)
-        if dts.dtype != xs.dtype or z.stride(-1) != 1 or z.stride(1) != z.shape[2] * z.stride(2):
+        if dts.dtype != xs.dtype:
             return None
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else xs.dtype
-        H, W = x.shape[2:]
         return fused.ss2d_core(xs, dts.contiguous(), As, Bs, Cs, self.Ds.float().view(-1),
                                self.dt_projs_bias.float().view(-1), z, self.out_norm.weight, self.out_norm.bias, H, W,
                                self.out_norm.eps, out_dtype)
+
+    def _folded_core(self, x: torch.Tensor, z: torch.Tensor):
+        """The fused core on the folded direction layout (nnuzoo_b200.fused.SS2DFoldedFn): the projections of m2net.py:179-182
+        are point-wise in L, so they are taken on the un-flipped arrays xs2 = {row-major, column-major} -- one GEMM per
+        array with the weights of its forward and its backward walker stacked -- and the scan walks directions 2 / 3
+        backwards instead of reading flipped copies.  Same values as `_scan_operands` + `ss2d_core`, fewer passes."""
+        N, R, D = self.d_state, self.dt_rank, self.d_inner
+        C = R + 2 * N
+        bsz, _, H, W = x.shape
+        perm = list(fused.FOLD_PERM)
+        xs2 = cross_scan_pair(x)                                                    # (B, 2, D, L)
+        wx = self.x_proj_weight[perm].reshape(2, 2 * C, D)                          # array a: directions a and a + 2
+        x_dbl = grouped_proj(xs2, wx).view(bsz, 4, C, H * W)                        # folded order, m2net.py:179
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                          # :181
+        dts = grouped_proj(dts, self.dt_projs_weight[perm])                         # :182
+        if dts.dtype != xs2.dtype:
+            return None
+        As = -torch.exp(self.A_logs.float()).view(4, D, N)[perm].reshape(4 * D, N)  # :190
+        Ds = self.Ds.float().view(4, D)[perm].reshape(-1)
+        bias = self.dt_projs_bias.float().view(4, D)[perm].reshape(-1)
+        out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else xs2.dtype
+        return fused.ss2d_core_folded(xs2, dts.contiguous(), As, Bs, Cs, Ds, bias, z, self.out_norm.weight,
+                                      self.out_norm.bias, H, W, self.out_norm.eps, out_dtype)
 
     def _finish(self, y, z, bsz, spatial):
         y = y.transpose(1, 2).contiguous().view(bsz, *spatial, -1)     # m2net.py:219

@@ -1,0 +1,163 @@
+"""GPU parity tests of the folded SS2D path: reversed groups / shared u rows in the scan (NzScanDesc::rev_mask, u_gdiv),
+the pair CrossScan, the folded epilogue layout and the SS2D module that uses them.
+
+Oracle chain: the flipped-copy formulation is the reference's own (m2net.py:175-177, :202-206); `selective_scan_fn`
+without the extension is pinned to the fp64 oracle and the reference-made goldens elsewhere (tests/test_scan_gpu.py), so
+here the folded call is checked (a) against the fp64 C oracle run on explicitly flipped copies and (b) against the
+un-folded module path, whose goldens come from the reference modules (tests/test_module_gpu.py, which now runs folded by
+default).  CrossScan data movement: bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"float32": 1e-3, "bfloat16": 2e-2}
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _unfold(t, G, rev_mask):
+    """(B, G*D, L) folded (un-flipped) -> the reference's view of it: reversed groups flipped along L."""
+    b, gd, L = t.shape
+    t = t.view(b, G, gd // G, L).clone()
+    for g in range(G):
+        if (rev_mask >> g) & 1:
+            t[:, g] = t[:, g].flip(-1)
+    return t.view(b, gd, L)
+
+
+def _folded_case(batch, D, L, seed, dt="float32"):
+    g = torch.Generator().manual_seed(seed)
+    G, N, n = 4, 16, 2
+    u2 = torch.randn(batch, (G // n) * D, L, generator=g)
+    delta = 0.5 * torch.randn(batch, G * D, L, generator=g)
+    A = -(torch.arange(1, N + 1).float().repeat(G * D, 1) * torch.exp(0.1 * torch.randn(G * D, N, generator=g)))
+    xdbl = torch.randn(batch, G, 5 + 2 * N, L, generator=g)   # B, C as split views of one projection (m2net.py:181)
+    Dp = 1.0 + 0.1 * torch.randn(G * D, generator=g)
+    dtv = torch.exp(torch.rand(G * D, generator=g) * (np.log(0.1) - np.log(0.001)) + np.log(0.001))
+    bias = dtv + torch.log(-torch.expm1(-dtv))
+    gout = torch.randn(batch, G * D, L, generator=g)
+    dtype = getattr(torch, dt)
+    return dict(u2=u2.to(dtype), delta=delta.to(dtype), A=A, xdbl=xdbl.to(dtype), D=Dp, bias=bias, gout=gout.to(dtype))
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 1024), (1, 64, 4128), (2, 32, 32), (1, 32, 16384)])
+def test_reversed_groups_match_the_oracle_on_flipped_copies(shape):
+    """rev_mask = 0b1010, u_gdiv = 2 (the SS2D layout) vs the fp64 oracle fed explicit flipped copies."""
+    from nnuzoo_b200.selective_scan_interface import SelectiveScanFn
+    from oracle import scan_oracle
+    batch, D, L = shape
+    c = _folded_case(batch, D, L, seed=7 + L)
+    G, N, rev = 4, 16, 0b1010
+    dev = _dev()
+    u2 = c["u2"].to(dev).requires_grad_(True)
+    delta = c["delta"].to(dev).requires_grad_(True)
+    A = c["A"].to(dev).requires_grad_(True)
+    xdbl = c["xdbl"].to(dev).requires_grad_(True)
+    B, C = xdbl[:, :, 5:5 + N], xdbl[:, :, 5 + N:]
+    Dp = c["D"].to(dev).requires_grad_(True)
+    bias = c["bias"].to(dev).requires_grad_(True)
+    out = SelectiveScanFn.apply(u2, delta, A, B, C, Dp, None, bias, True, False, None, rev, 2)
+    out.backward(c["gout"].to(dev))
+    torch.cuda.synchronize()
+
+    # the reference formulation on the CPU: materialise the four directions, flipped where the mask says so
+    u_full = c["u2"].view(batch, 2, D, L).repeat_interleave(2, dim=1).reshape(batch, G * D, L)
+    fl = lambda t: _unfold(t.float(), G, rev)  # noqa: E731
+    Bc, Cc = c["xdbl"][:, :, 5:5 + N].float(), c["xdbl"][:, :, 5 + N:].float()
+    flg = lambda t: torch.stack([t[:, g].flip(-1) if (rev >> g) & 1 else t[:, g] for g in range(G)], 1)  # noqa: E731
+    r_u, r_dl, r_B, r_C, r_go = fl(u_full), fl(c["delta"]), flg(Bc), flg(Cc), fl(c["gout"])
+    ref_out = scan_oracle.selective_scan_oracle(r_u, r_dl, c["A"], r_B, r_C, c["D"], None, c["bias"],
+                                                delta_softplus=True, return_last_state=False, precision="f64")
+    ref_g = scan_oracle.selective_scan_oracle_bwd(r_u, r_dl, c["A"], r_B, r_C, c["D"], None, c["bias"], True, r_go,
+                                                  precision="f64")
+    as_t = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float64)  # noqa: E731
+    errs = {"out": rel_err(out.detach().cpu().numpy(), fl(as_t(ref_out).float()).numpy())}
+    du_ref = fl(as_t(ref_g["du"]).float()).view(batch, 2, 2, D, L).sum(2).view(batch, 2 * D, L)
+    errs["du"] = rel_err(u2.grad.cpu().numpy(), du_ref.numpy())
+    errs["ddelta"] = rel_err(delta.grad.cpu().numpy(), fl(as_t(ref_g["ddelta"]).float()).numpy())
+    dB_ref, dC_ref = flg(as_t(ref_g["dB"]).float()), flg(as_t(ref_g["dC"]).float())
+    errs["dB"] = rel_err(xdbl.grad[:, :, 5:5 + N].cpu().numpy(), dB_ref.numpy())
+    errs["dC"] = rel_err(xdbl.grad[:, :, 5 + N:].cpu().numpy(), dC_ref.numpy())
+    errs["dA"] = rel_err(A.grad.cpu().numpy(), np.asarray(ref_g["dA"]))
+    errs["dD"] = rel_err(Dp.grad.cpu().numpy(), np.asarray(ref_g["dD"]))
+    errs["dbias"] = rel_err(bias.grad.cpu().numpy(), np.asarray(ref_g["ddelta_bias"]))
+    bad = {k: v for k, v in errs.items() if not v < TOL["float32"]}
+    assert not bad, f"folded scan {shape}: {errs}"
+
+
+def test_folded_scan_is_refused_where_the_row_per_lane_kernels_do_not_apply():
+    from nnuzoo_b200.selective_scan_interface import SelectiveScanFn
+    c = _folded_case(1, 16, 128, seed=3)     # 16 rows per group: not a multiple of 32
+    dev = _dev()
+    N = 16
+    xdbl = c["xdbl"].to(dev)
+    with pytest.raises(RuntimeError, match="row-per-lane"):
+        SelectiveScanFn.apply(c["u2"].to(dev), c["delta"].to(dev), c["A"].to(dev), xdbl[:, :, 5:5 + N], xdbl[:, :, 5 + N:],
+                              c["D"].to(dev), None, c["bias"].to(dev), True, False, None, 0b1010, 2)
+
+
+@pytest.mark.parametrize("dt", ["float32", "bfloat16"])
+@pytest.mark.parametrize("hw", [(32, 48), (16, 16), (40, 24)])
+def test_cross_scan_pair_is_bit_exact_and_adjoint(hw, dt):
+    from nnuzoo_b200.cross_scan import cross_scan, cross_scan_pair
+    H, W = hw
+    dtype = getattr(torch, dt)
+    g = torch.Generator().manual_seed(H * 100 + W)
+    x = torch.randn(2, 8, H, W, generator=g).to(dtype).to(_dev()).requires_grad_(True)
+    xs2 = cross_scan_pair(x)
+    xs4 = cross_scan(x.detach())
+    assert torch.equal(xs2[:, 0], xs4[:, 0]) and torch.equal(xs2[:, 1], xs4[:, 1])
+    assert torch.equal(xs2[:, 0].flip(-1), xs4[:, 2]) and torch.equal(xs2[:, 1].flip(-1), xs4[:, 3])
+    gy = torch.randn(2, 2, 8, H * W, generator=g).to(dtype).to(_dev())
+    xs2.backward(gy)
+    ref = (gy[:, 0].float().view(2, 8, H, W) + gy[:, 1].float().view(2, 8, W, H).transpose(2, 3)).to(dtype)
+    assert torch.equal(x.grad, ref)
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+@pytest.mark.parametrize("cfg", [(16, 32, 32), (32, 16, 48), (64, 16, 16)])
+def test_ss2d_folded_equals_unfolded(cfg, autocast):
+    """The same module with and without direction folding: merged values are the same numbers in the same order; the
+    scan's own reassociation differs between a flipped copy and a backward walk only by rounding."""
+    from nnuzoo_b200.ss2d import SS2D
+    d_model, H, W = cfg
+    torch.manual_seed(d_model + H)
+    m = SS2D(d_model).to(_dev())
+    x = torch.randn(2, H, W, d_model, device=_dev())
+    outs, grads = [], []
+    for fold in (True, False):
+        m.fold_directions = fold
+        m.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = m(xi)
+        y.float().square().mean().backward()
+        outs.append(y.detach().float())
+        grads.append({"x": xi.grad.float(), **{n: p.grad.float().clone() for n, p in m.named_parameters()}})
+    tol = 3e-2 if autocast else 2e-3
+    assert rel_err(outs[0].cpu().numpy(), outs[1].cpu().numpy()) < tol
+    for k in grads[0]:
+        e = rel_err(grads[0][k].cpu().numpy(), grads[1][k].cpu().numpy())
+        assert e < tol, f"grad {k}: {e}"
+
+
+def test_ss2d_folded_forward_launches_no_flip_kernels():
+    """Launch accounting of one SS2D forward under no_grad: pair scan (1) + scan (1-3) + epilogue (1) + dwconv (1)."""
+    from nnuzoo_b200 import _native
+    from nnuzoo_b200.ss2d import SS2D
+    torch.manual_seed(0)
+    m = SS2D(16).to(_dev()).eval()
+    x = torch.randn(1, 32, 32, 16, device=_dev())
+    with torch.no_grad():
+        m(x)
+        n0 = _native.launch_count()
+        m(x)
+        n1 = _native.launch_count()
+    assert n1 - n0 <= 6, n1 - n0

@@ -55,6 +55,12 @@ def test_fused_path_is_actually_taken():
     x = torch.randn(1, 8, 8, 16, device="cuda")
     n0 = _native.launch_count()
     mod(x)
+    folded_launches = _native.launch_count() - n0
+    # folded (the default): dwconv, pair scan, scan (1, or 3 chunk-parallel), folded epilogue
+    assert 4 <= folded_launches <= 6
+    mod.fold_directions = False
+    n0 = _native.launch_count()
+    mod(x)
     fused_launches = _native.launch_count() - n0
     mod.fuse_epilogue = False
     n0 = _native.launch_count()
