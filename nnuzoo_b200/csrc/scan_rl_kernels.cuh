@@ -769,9 +769,12 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
   const int j_lo = t_lo * NBLK, j_hi = t_hi * NBLK;  // fine blocks [j_lo, j_hi), walked last to first
   const bool rev = kRevCap && ((a.rev_mask >> g) & 1);              // the forward walked this group backwards
   const int ur = kRevCap ? (g / a.u_gdiv) * a.dpg + rb * 32 : d0;   // rows of u
-  const int nblk = j_hi - j_lo;
-  auto jof = [&](int k) { return rev ? j_lo + k : j_hi - 1 - k; };  // k-th block in walking order
-  const int jprev = rev ? 1 : -1;  // the block whose end state enters block j lies at j + jprev
+  // Walking order of the blocks: last to first, or first to last for a reversed group.  (Block indices are stepped, not
+  // derived from a trip counter: with `jb = f(k)` ptxas moved the counter into a uniform register and the kernel then
+  // produced sparse, run-to-run different errors at 1 MB row pitch -- profiles/r02_kernel_tuning.md.)
+  const int step = rev ? 1 : -1;
+  const int j_first = rev ? j_lo : j_hi - 1;
+  auto inside = [&](int j) { return j >= j_lo && j < j_hi; };
 
   auto issue_rows = [&](int j, int s) {
     uint8_t* st = smem + s * SM::RSTAGE;
@@ -780,7 +783,7 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
     tma_load_4d(st + RB, &a.tm_delta, &bars[s], 0, j, d0, b);
     tma_load_4d(st + 2 * RB, &a.tm_dout, &bars[s], 0, j, d0, b);
     if (kHasZ) tma_load_4d(st + 3 * RB, &a.tm_z, &bars[s], 0, j, d0, b);
-    tma_load_4d(st + SM::OFF_XF, &a.tm_xf, &bars[s], 0, j + jprev, d0, b);  // out of bounds (first block): zero fill
+    tma_load_4d(st + SM::OFF_XF, &a.tm_xf, &bars[s], 0, j + step, d0, b);  // the block the FORWARD walked before j; out of bounds: zero fill
   };
   auto issue_bc = [&](int j, int s) {
     uint8_t* st = smem + SM::OFF_BC + s * SM::BSTAGE;
@@ -792,11 +795,11 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-    issue_rows(jof(0), 0);
-    issue_bc(jof(0), 0);
-    if (nblk > 1) {
-      issue_rows(jof(1), 1);
-      issue_bc(jof(1), 1);
+    issue_rows(j_first, 0);
+    issue_bc(j_first, 0);
+    if (inside(j_first + step)) {
+      issue_rows(j_first + step, 1);
+      issue_bc(j_first + step, 1);
     }
   }
   __syncwarp();
@@ -830,9 +833,9 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
   long Lq = a.L * 16;  // byte pitch of four state rows of dB / dC
   asm volatile("" : "+l"(Lq));
 
+  int k = 0;
 #pragma unroll 1
-  for (int k = 0; k < nblk; ++k) {
-    const int jb = jof(k);
+  for (int jb = j_first; inside(jb); jb += step, ++k) {
     const int s = k & 1;
     const uint32_t ph = (uint32_t)(k >> 1) & 1u;
     mbar_wait(&bars[s], ph);
@@ -875,7 +878,7 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
     }
     // this stage's row data now lives in registers: request the block after the next one into it
     __syncwarp();
-    if (lane == 0 && k + 2 < nblk) issue_rows(jof(k + 2), s);
+    if (lane == 0 && inside(jb + 2 * step)) issue_rows(jb + 2 * step, s);
     mbar_wait(&bars[2 + s], ph);
     const uint32_t tB = bc_s + s * SM::BSTAGE;
     uint32_t tbj[4];
@@ -1002,7 +1005,7 @@ __global__ void NZ_RL_BWD2_BOUNDS scan_bwd_rl2_kernel(const __grid_constant__ Rl
       states(std::false_type{});
     }
     __syncwarp();  // every lane is done with B/C stage s
-    if (lane == 0 && k + 2 < nblk) issue_bc(jof(k + 2), s);
+    if (lane == 0 && inside(jb + 2 * step)) issue_bc(jb + 2 * step, s);
 
     // ---- per-(row, t) epilogue of the block ----
     const long tpos = (long)jb * kFine;
@@ -1078,8 +1081,9 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
   const long nbt = a.L / kFine;
   const bool rev = kRevCap && ((a.rev_mask >> g) & 1);              // this group walks the sequence backwards
   const int ur = kRevCap ? (g / a.u_gdiv) * a.dpg + rb * 32 : d0;   // rows of u
-  const int nblk = j_hi - j_lo;
-  auto jof = [&](int k) { return rev ? j_hi - 1 - k : j_lo + k; };  // k-th block in walking order
+  const int step = rev ? -1 : 1;  // walking order of the blocks (stepped block index, see scan_bwd_rl2_kernel)
+  const int j_first = rev ? j_hi - 1 : j_lo;
+  auto inside = [&](int j) { return j >= j_lo && j < j_hi; };
 
   auto issue = [&](int j, int s) {
     uint8_t* st = smem + s * SM::RSTAGE;
@@ -1096,8 +1100,8 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
 #pragma unroll
     for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-    issue(jof(0), 0);
-    if (nblk > 1) issue(jof(1), 1);
+    issue(j_first, 0);
+    if (inside(j_first + step)) issue(j_first + step, 1);
   }
   __syncwarp();
   float A2[kMaxState], h[kMaxState];
@@ -1117,9 +1121,9 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
   for (int n = 0; n < kMaxState; ++n) amax = fmaxf(amax, fabsf(A2[n]));
   const float dlim = 126.f / fmaxf(amax, 1e-30f);  // |A2 * dl| <= 126 for the exponent arithmetic of ex2_poly2
 
+  int k = 0;
 #pragma unroll 1
-  for (int k = 0; k < nblk; ++k) {
-    const int jb = jof(k);
+  for (int jb = j_first; inside(jb); jb += step, ++k) {
     const int s = k & 1;
     const uint32_t ph = (uint32_t)(k >> 1) & 1u;
     mbar_wait(&bars[s], ph);
@@ -1185,7 +1189,7 @@ __global__ void __launch_bounds__(32, NZ_RL_FWD_MINB) scan_fwd_rl_kernel(const _
     }
     // every lane is done with this block's stages: request the block after the next one
     __syncwarp();
-    if (lane == 0 && k + 2 < nblk) issue(jof(k + 2), s);
+    if (lane == 0 && inside(jb + 2 * step)) issue(jb + 2 * step, s);
     if constexpr (kHasZ) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] *= zz[i] * sigmoid_f(zz[i]);

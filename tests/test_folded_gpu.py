@@ -161,3 +161,43 @@ def test_ss2d_folded_forward_launches_no_flip_kernels():
         m(x)
         n1 = _native.launch_count()
     assert n1 - n0 <= 6, n1 - n0
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 262144), (12, 32, 16384)])
+def test_folded_scan_equals_flipped_copies_at_full_size(shape):
+    """The stage-1 row length (1 MB rows, thousands of chunks): folded call vs the plain call on materialised flipped
+    copies, GPU against GPU.  (A first version of the reversed-capable kernels failed only here, sparsely and differently
+    from run to run; the small oracle cases above did not see it.)"""
+    from nnuzoo_b200.selective_scan_interface import SelectiveScanFn
+    batch, D, L = shape
+    dev = _dev()
+    G, N, rev = 4, 16, 0b1010
+    g = torch.Generator(device=dev).manual_seed(L + D)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)  # noqa: E731
+    u2 = rnd(batch, 2 * D, L).requires_grad_(True)
+    delta = (0.5 * rnd(batch, G * D, L)).requires_grad_(True)
+    A = (-torch.arange(1, N + 1, device=dev).float().repeat(G * D, 1)).requires_grad_(True)
+    B = rnd(batch, G, N, L).requires_grad_(True)
+    C = rnd(batch, G, N, L).requires_grad_(True)
+    Dp = torch.ones(G * D, device=dev).requires_grad_(True)
+    bias = torch.full((G * D,), -3.0, device=dev).requires_grad_(True)
+    gout = rnd(batch, G * D, L)
+    leaves = (u2, delta, A, B, C, Dp, bias)
+    out = SelectiveScanFn.apply(u2, delta, A, B, C, Dp, None, bias, True, False, None, rev, 2)
+    out.backward(gout)
+    got = [out.detach()] + [t.grad.clone() for t in leaves]
+    for t in leaves:
+        t.grad = None
+
+    def fl(t, groups_dim=1):  # flip the reversed groups of a (B, G, X, L) tensor along L
+        return torch.stack([t[:, k].flip(-1) if (rev >> k) & 1 else t[:, k] for k in range(G)], groups_dim)
+    u4 = u2.view(batch, 2, D, L).repeat_interleave(2, dim=1)
+    out_ref = SelectiveScanFn.apply(fl(u4).reshape(batch, G * D, L), fl(delta.view(batch, G, D, L)).reshape(batch, G * D, L),
+                                    A, fl(B), fl(C), Dp, None, bias, True, False, None)
+    out_ref = fl(out_ref.view(batch, G, D, L)).reshape(batch, G * D, L)
+    out_ref.backward(gout)
+    ref = [out_ref.detach()] + [t.grad for t in leaves]
+    torch.cuda.synchronize()
+    names = ["out", "du", "ddelta", "dA", "dB", "dC", "dD", "dbias"]
+    errs = {n: float((a - r).abs().max() / r.abs().max()) for n, a, r in zip(names, got, ref)}
+    assert all(v < 1e-3 for v in errs.values()), errs
