@@ -86,8 +86,9 @@ class SS2DCoreFn(torch.autograd.Function):
             dout = dout.to(out_dtype)
         d_out_y = torch.empty((bsz, K * D, L), dtype=op_dtype, device=dev)   # the scan's operand dtype
         dz = torch.empty((bsz, H, W, D), dtype=z.dtype, device=dev)
-        dg = torch.zeros(D, dtype=torch.float32, device=dev) if g32 is not None else None
-        db = torch.zeros(D, dtype=torch.float32, device=dev) if b32 is not None else None
+        dgb = torch.zeros(2 * D, dtype=torch.float32, device=dev)
+        dg = dgb[:D] if g32 is not None else None
+        db = dgb[D:] if b32 is not None else None
         zs = (ctypes.c_int64 * 2)(z.stride(0), z.stride(2))
         _native.bind_device(dev.index)
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
@@ -159,8 +160,9 @@ class SS2DFoldedFn(torch.autograd.Function):
             dout = dout.to(out_dtype)
         d_out_y = torch.empty((bsz, K * D, L), dtype=op_dtype, device=dev)   # the scan's operand dtype, folded layout
         dz = torch.empty((bsz, H, W, D), dtype=z.dtype, device=dev)
-        dg = torch.zeros(D, dtype=torch.float32, device=dev) if g32 is not None else None
-        db = torch.zeros(D, dtype=torch.float32, device=dev) if b32 is not None else None
+        dgb = torch.zeros(2 * D, dtype=torch.float32, device=dev)
+        dg = dgb[:D] if g32 is not None else None
+        db = dgb[D:] if b32 is not None else None
         zs = (ctypes.c_int64 * 2)(z.stride(0), z.stride(2))
         _native.bind_device(dev.index)
         st = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)

@@ -186,9 +186,11 @@ class SelectiveScanFn(torch.autograd.Function):
         du = torch.empty((batch, dim, L), dtype=u.dtype, device=dev)
         ddelta = torch.empty_like(du)
         dz = torch.empty_like(du) if ctx.has_z else None
-        dA = torch.zeros((dim, N), dtype=torch.float32, device=dev)
-        dD = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_D else None
-        dbias = torch.zeros((dim,), dtype=torch.float32, device=dev) if ctx.has_bias else None
+        # the three (dim)-shaped accumulators share one zero fill
+        acc = torch.zeros((N + 2) * dim, dtype=torch.float32, device=dev)
+        dA = acc[:dim * N].view(dim, N)
+        dD = acc[dim * N:dim * (N + 1)] if ctx.has_D else None
+        dbias = acc[dim * (N + 1):] if ctx.has_bias else None
         desc = NzScanDesc()
         ws = _fill_common(desc, u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus, _FORCE_GENERIC, xf=xf,
                           rev_mask=ctx.fold[0], u_gdiv=ctx.fold[1])

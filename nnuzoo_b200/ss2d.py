@@ -179,17 +179,22 @@ class _CrossScanSSM(nn.Module):
         N, R, D = self.d_state, self.dt_rank, self.d_inner
         C = R + 2 * N
         bsz, _, H, W = x.shape
-        perm = list(fused.FOLD_PERM)
+
+        def fold(p, *tail):
+            # reference direction k = 2 * backwards + array  ->  folded k' = 2 * array + backwards (fused.FOLD_PERM):
+            # a transpose of the (2, 2) factorisation of the direction axis, one small copy
+            return p.view(2, 2, *tail).transpose(0, 1)
+
         xs2 = cross_scan_pair(x)                                                    # (B, 2, D, L)
-        wx = self.x_proj_weight[perm].reshape(2, 2 * C, D)                          # array a: directions a and a + 2
+        wx = fold(self.x_proj_weight, C, D).reshape(2, 2 * C, D)                    # array a: directions a and a + 2
         x_dbl = grouped_proj(xs2, wx).view(bsz, 4, C, H * W)                        # folded order, m2net.py:179
         dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                          # :181
-        dts = grouped_proj(dts, self.dt_projs_weight[perm])                         # :182
+        dts = grouped_proj(dts, fold(self.dt_projs_weight, D, R).reshape(4, D, R))  # :182
         if dts.dtype != xs2.dtype:
             return None
-        As = -torch.exp(self.A_logs.float()).view(4, D, N)[perm].reshape(4 * D, N)  # :190
-        Ds = self.Ds.float().view(4, D)[perm].reshape(-1)
-        bias = self.dt_projs_bias.float().view(4, D)[perm].reshape(-1)
+        As = -torch.exp(fold(self.A_logs.float(), D, N)).reshape(4 * D, N)          # :190
+        Ds = fold(self.Ds.float(), D).reshape(-1)
+        bias = fold(self.dt_projs_bias.float(), D).reshape(-1)
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else xs2.dtype
         return fused.ss2d_core_folded(xs2, dts.contiguous(), As, Bs, Cs, Ds, bias, z, self.out_norm.weight,
                                       self.out_norm.bias, H, W, self.out_norm.eps, out_dtype)
