@@ -140,6 +140,19 @@ static bool tma_ok_rows(const void* p, int dtype, int64_t L, const int64_t* dims
   return true;
 }
 
+// SM count of the current device, asked once per device
+static int sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] <= 0) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = sms;
+  }
+  return cached[dev];
+}
+
 static inline bool folded(const NzScanDesc* d) { return d->rev_mask != 0 || d->u_gdiv > 1; }
 static inline int u_gdiv(const NzScanDesc* d) { return d->u_gdiv > 1 ? d->u_gdiv : 1; }
 
@@ -205,8 +218,7 @@ static void fill_args(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
   a.skew = -1;
   // chain-limited launches (far fewer row blocks than the 2 resident CTAs per SM) claim tickets just in time
   {
-    int dev = 0, sms = 148;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     a.claim_late = a.nrb_total <= sms / 2 ? 1 : 0;  // measured: 1.3-1.7x at 8 row blocks, neutral at 96, -5 % at 192
   }
   if (const char* e = getenv("NZ_CLAIM_LATE")) a.claim_late = atoi(e);  // tuning override
@@ -261,8 +273,7 @@ static bool setup_tma(const NzScanDesc* d, ScanKArgs& a, bool bwd) {
 // (row, state) -- h_in[c+1] = fma(P_c, h_in[c], H_c), the very operation the chained kernel performs, so the results are
 // bit-identical -- and the final pass with every tile on the fast path.
 static bool cp_eligible(const NzScanDesc* d) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int dpg = d->dim / (d->ngroups > 0 ? d->ngroups : 1);
   const long nrb_total = (long)d->batch * d->ngroups * ((dpg + kFwdRows - 1) / kFwdRows);
   const long nchunks = (d->seqlen + kFwdTL - 1) / kFwdTL;
@@ -379,8 +390,7 @@ static bool rl_shape_ok(const NzScanDesc* d) {
 // would do: profiles/r02_kernel_tuning.md), each chunk a whole number of 128-byte tiles.  `resident` = warps per SM of
 // the main pass (backward 12, forward 16).
 static void rl_plan(const NzScanDesc* d, int* nchunks, int* tpc, int resident = 12) {
-  int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const long rbt = (long)d->batch * (d->dim / 32);
   const long ntl = d->seqlen * (long)esize(d->dtype) / 128;
   long target = 6L * sms * resident;

@@ -28,18 +28,29 @@ constexpr int kWarps = 8;
 constexpr int kFwdRows = (32 / NZ_FWD_LPR) * kWarps, kFwdTL = NZ_FWD_M * NZ_FWD_LPR;
 constexpr int kBwdRows = (32 / NZ_BWD_LPR) * kWarps, kBwdTL = NZ_BWD_M * NZ_BWD_LPR;
 
-// Persistent grid: as many CTAs as fit on the device (or as there are tiles).
+// Persistent grid: as many CTAs as fit on the device (or as there are tiles).  The per-kernel facts behind it -- the
+// dynamic shared-memory opt-in and the resident CTAs per SM -- are asked of the driver once per kernel instantiation and
+// device, not on every call (BASELINE configs[3] makes hundreds of ~10 us scans per step).
+constexpr int kMaxDevices = 64;
 template <typename K>
-static cudaError_t persistent_grid(K kern, int threads, size_t smem, int ntiles, unsigned* grid) {
-  int dev = 0, sms = 0, per_sm = 0;
+static cudaError_t persistent_grid(K kern, int threads, size_t smem, int ntiles, unsigned* grid, int* cache) {
+  int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
-  e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) return e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  const long cap = (long)sms * per_sm;
+  int* slot = (dev >= 0 && dev < kMaxDevices) ? &cache[dev] : nullptr;
+  int cap = slot ? *slot : 0;
+  if (cap <= 0) {
+    int sms = 0, per_sm = 0;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    cap = sms * per_sm;
+    if (slot) *slot = cap;
+  }
   *grid = (unsigned)(ntiles < cap ? ntiles : cap);
   return cudaSuccess;
 }
@@ -52,10 +63,9 @@ static cudaError_t launch_fwd_one(const ScanKArgs& a, cudaStream_t st) {
   using Cfg = ScanCfg<T, NZ_FWD_M, NZ_FWD_LPR, kWarps, kHasZ, false>;
   auto kern = scan_fwd_kernel<T, NZ_FWD_M, NZ_FWD_LPR, kWarps, NZ_FWD_NQ, kTMA, kHasZ, kFineCk>;
   const size_t smem = Cfg::smem_bytes(kTMA, kFineCk);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static int cache[kMaxDevices] = {};
   unsigned grid = 0;
-  e = persistent_grid(kern, kWarps * 32, smem, a.ntiles, &grid);
+  cudaError_t e = persistent_grid(kern, kWarps * 32, smem, a.ntiles, &grid, cache);
   if (e != cudaSuccess) return e;
   kern<<<grid, kWarps * 32, smem, st>>>(a);
   return cudaGetLastError();
@@ -66,10 +76,9 @@ static cudaError_t launch_bwd_one(const ScanKArgs& a, cudaStream_t st) {
   using Cfg = ScanCfg<T, NZ_BWD_M, NZ_BWD_LPR, kWarps, kHasZ, true>;
   auto kern = scan_bwd_kernel<T, NZ_BWD_M, NZ_BWD_LPR, kWarps, kTMA, kHasZ>;
   const size_t smem = Cfg::smem_bytes(kTMA);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  static int cache[kMaxDevices] = {};
   unsigned grid = 0;
-  e = persistent_grid(kern, kWarps * 32, smem, a.ntiles, &grid);
+  cudaError_t e = persistent_grid(kern, kWarps * 32, smem, a.ntiles, &grid, cache);
   if (e != cudaSuccess) return e;
   kern<<<grid, kWarps * 32, smem, st>>>(a);
   return cudaGetLastError();

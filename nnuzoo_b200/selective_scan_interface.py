@@ -231,4 +231,9 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     the reference first copies xs / dts / Bs / Cs to fp32 (m2net.py:185-188) to get an fp32 out_y (:200).  The
     arithmetic is the same fp32 arithmetic on the same operand values; the backward reads ``dout`` in the operand
     dtype."""
+    if torch.compiler.is_compiling():
+        # under torch.compile (the reference's default, nnUNetTrainer.py:316-322) the scan is one opaque custom op with
+        # a fake implementation and an autograd formula (nnuzoo_b200/library_ops.py) instead of a graph break
+        from .library_ops import selective_scan_compiled
+        return selective_scan_compiled(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state, out_dtype)
     return SelectiveScanFn.apply(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state, out_dtype)

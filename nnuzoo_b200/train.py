@@ -117,7 +117,8 @@ class Trainer:
     """One nnUNetTrainerM2Net-style optimisation step on this rank's share of the batch."""
 
     def __init__(self, network: nn.Module, device, ddp: bool | None = None, sync_bn: bool = False,
-                 autocast_dtype=torch.bfloat16, lr=1e-4, weight_decay=5e-2, batch_dice=True, clip=12.0):
+                 autocast_dtype=torch.bfloat16, lr=1e-4, weight_decay=5e-2, batch_dice=True, clip=12.0,
+                 cuda_graph: bool = False):
         self.device = torch.device(device)
         self.ddp = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 if ddp is None else ddp
         if sync_bn and self.ddp:
@@ -133,16 +134,62 @@ class Trainer:
         n_out = 7 if getattr(self.module, "deep_supervision", False) else 1
         base = DiceCELoss(batch_dice=batch_dice, ddp=self.ddp)
         self.loss = DeepSupervisionLoss(base, deep_supervision_weights(n_out, self.ddp)) if n_out > 1 else base
+        # cuda_graph: the whole step (forward, loss, backward, clip, AdamW) is captured once into a CUDA graph and replayed:
+        # an M2Net step is ~12 500 kernels and 80 SS2D blocks of ~1.5 ms host time each, so the eager step is bound by the
+        # host, not by the GPU.  Static shapes only (nnU-Net patches are); the first `graph_warmup` steps run eagerly.
+        self.cuda_graph = bool(cuda_graph) and self.device.type == "cuda" and autocast_dtype != torch.float16
+        self._graph, self._static, self._steps, self.graph_warmup, self.graph_error = None, None, 0, 3, None
         self.optimizer = torch.optim.AdamW(self.module.parameters(), lr=lr, weight_decay=weight_decay, eps=1e-5,
-                                           betas=(0.9, 0.999))
+                                           betas=(0.9, 0.999), capturable=self.cuda_graph)
         self.autocast_dtype, self.clip = autocast_dtype, clip
         # fp16 autocast needs the reference's loss scaling (nnUNetTrainer.py:1128-1139); bf16 does not
         self.scaler = (torch.amp.GradScaler(self.device.type) if autocast_dtype == torch.float16 and
                        self.device.type == "cuda" else None)
 
+    def _eager_step(self, data, target) -> torch.Tensor:
+        dev = self.device
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.autocast(dev.type, dtype=self.autocast_dtype, enabled=dev.type == "cuda"):
+            out = self.network(data)
+            loss = self.loss(out, target)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.module.parameters(), self.clip)
+        self.optimizer.step()
+        return loss.detach()
+
+    def _graphed_step(self, data, target) -> torch.Tensor:
+        """Replay (after capturing once) the whole optimisation step on static input buffers."""
+        targets = list(target) if isinstance(target, (list, tuple)) else [target]
+        if self._graph is None:
+            self._static = (torch.empty(data.shape, dtype=data.dtype, device=self.device),
+                            [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in targets])
+        s_data, s_targets = self._static
+        s_data.copy_(data, non_blocking=True)
+        for dst, src in zip(s_targets, targets):
+            dst.copy_(src, non_blocking=True)
+        if self._graph is None:
+            tgt = s_targets if isinstance(target, (list, tuple)) else s_targets[0]
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                self._static_loss = self._eager_step(s_data, tgt)
+            self._graph = graph
+        self._graph.replay()
+        return self._static_loss
+
     def train_step(self, data: torch.Tensor, target) -> torch.Tensor:
         """``data`` / ``target`` may be (pinned) host tensors; returns the detached loss on the device."""
         dev = self.device
+        self._steps += 1
+        if self.cuda_graph and self._steps > self.graph_warmup and self.graph_error is None:
+            try:
+                return self._graphed_step(data, target)   # copies the (host) batch straight into the static buffers
+            except Exception as e:  # capture refused (an op that synchronises, a collective that cannot be captured...)
+                if self._graph is not None:
+                    raise
+                self.graph_error = f"{type(e).__name__}: {e}"[:300]
+                torch.cuda.synchronize(dev)
         data = data.to(dev, non_blocking=True)
         if isinstance(target, (list, tuple)):
             target = [t.to(dev, non_blocking=True) for t in target]
