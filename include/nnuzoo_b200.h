@@ -210,7 +210,10 @@ typedef struct NzConv1dDesc {
   int32_t batch, dim, width, dtype; /* dtype of x / out / dout / dx: NZ_F32 / NZ_BF16 / NZ_F16 */
   int64_t seqlen;
   int32_t silu;                     /* 1: SiLU activation fused, 0: plain convolution */
-  int32_t reserved0;
+  int32_t reverse;                  /* 1: the convolution of the L-flipped sequence, written un-flipped:
+                                       out[l] = act(bias + sum_k w[k] x[l + (W-1) - k]), x = 0 right of the sequence
+                                       (what `conv1d(x.flip(-1)).flip(-1)` computes: mamba_simple.py:250-262,
+                                       mamba_nd2net.py:638-641) -- the flipped copies are never made */
   const void* x;                    /* (batch, dim, L) */
   const float* weight;              /* (dim, W) fp32 */
   const float* bias;                /* (dim) fp32 or NULL */

@@ -52,7 +52,7 @@ class NzConv1dDesc(ctypes.Structure):
     _fields_ = [
         ("batch", _i32), ("dim", _i32), ("width", _i32), ("dtype", _i32),
         ("seqlen", _i64),
-        ("silu", _i32), ("reserved0", _i32),
+        ("silu", _i32), ("reverse", _i32),
         ("x", _vp), ("weight", _vp), ("bias", _vp), ("out", _vp), ("dout", _vp), ("dx", _vp),
         ("dweight", _vp), ("dbias", _vp),
         ("x_stride", _i64 * 2), ("out_stride", _i64 * 2), ("dout_stride", _i64 * 2),

@@ -114,7 +114,23 @@ struct ConvCh {
   static constexpr int STEPS = CH * kConvVec;  // steps per thread
 };
 
-template <typename T>
+// REV = the same convolution run over the L-flipped sequence without materialising the flip (the reversed Mamba
+// directions: mamba_simple.py:250-262 `xz.flip([-1])`, mamba_nd2net.py:638-641 `hidden_states.flip(1)`):
+//   out[l] = act(bias + sum_k w[k] x[l + (W-1) - k]),  x = 0 right of the sequence.
+// In the thread's mirrored step index i' = STEPS-1-i this IS the causal convolution, so the window is loaded from the
+// other side and reversed in registers (static indices, free), the arithmetic below is shared, and the results are
+// written back un-mirrored.
+template <int N>
+__device__ __forceinline__ void reverse_regs(float (&v)[N]) {
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    const float t = v[j];
+    v[j] = v[N - 1 - j];
+    v[N - 1 - j] = t;
+  }
+}
+
+template <typename T, bool REV>
 __global__ void __launch_bounds__(kConvThreads) conv1d_fwd_kernel(const ConvArgs a) {
   constexpr int CH = ConvCh<T>::CH, STEPS = ConvCh<T>::STEPS;
   const long nblk_l = (a.L + kConvThreads * STEPS - 1) / (kConvThreads * STEPS);
@@ -128,34 +144,40 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_fwd_kernel(const ConvArgs
 #pragma unroll
   for (int k = 0; k < kConvMaxW; ++k) w[k] = k < a.width ? __ldg(a.w + (long)d * a.width + k) : 0.f;
   const float bias = a.bias ? __ldg(a.bias + d) : 0.f;
-  float v[4 * (CH + 1)];  // x[l0 - 4 .. l0 + STEPS)
-  load_window<T, 1, CH - 1>(xr, l0, a.L, a.vec != 0, v);
+  float v[4 * (CH + 1)];  // x[l0 - 4 .. l0 + STEPS); REV: x[l0 .. l0 + STEPS + 4) mirrored
+  if (!REV) {
+    load_window<T, 1, CH - 1>(xr, l0, a.L, a.vec != 0, v);
+  } else {
+    load_window<T, 0, CH>(xr, l0, a.L, a.vec != 0, v);
+    reverse_regs(v);
+  }
   const int sh = kConvMaxW - a.width;  // taps are right-aligned: tap k multiplies x[l - (W-1) + k]
+  float o[STEPS];
+#pragma unroll
+  for (int i = 0; i < STEPS; ++i) {
+    float p = bias;
+#pragma unroll
+    for (int k = 0; k < kConvMaxW; ++k) {
+      const int kk = k - sh;  // index into w when width < kConvMaxW
+      if (kk >= 0) p = fmaf(w[kk], v[1 + i + k], p);
+    }
+    o[i] = a.silu ? silu_f(p) : p;
+  }
+  if (REV) reverse_regs(o);
 #pragma unroll
   for (int cch = 0; cch < CH; ++cch) {
-    float o[kConvVec];
-#pragma unroll
-    for (int i = 0; i < kConvVec; ++i) {
-      float p = bias;
-#pragma unroll
-      for (int k = 0; k < kConvMaxW; ++k) {
-        const int kk = k - sh;  // index into w when width < kConvMaxW
-        if (kk >= 0) p = fmaf(w[kk], v[4 * cch + 1 + i + k], p);
-      }
-      o[i] = a.silu ? silu_f(p) : p;
-    }
     const long lc = l0 + 4 * cch;
     if (a.vec) {
-      if (lc < a.L) store4<T>(orow + lc, o);
+      if (lc < a.L) store4<T>(orow + lc, &o[4 * cch]);
     } else {
 #pragma unroll
       for (int i = 0; i < kConvVec; ++i)
-        if (lc + i < a.L) orow[lc + i] = Elem<T>::from_f(o[i]);
+        if (lc + i < a.L) orow[lc + i] = Elem<T>::from_f(o[4 * cch + i]);
     }
   }
 }
 
-template <typename T>
+template <typename T, bool REV>
 __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const ConvArgs a) {
   constexpr int CH = ConvCh<T>::CH, STEPS = ConvCh<T>::STEPS;
   __shared__ float red[kConvThreads / 32][kConvMaxW + 1];
@@ -176,9 +198,15 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const ConvArgs
   if (l0 < a.L) {
     float xw[4 * (CH + 2)];                                // x[l0 - 4 .. l0 + STEPS + 4)
     load_window<T, 1, CH>(xr, l0, a.L, a.vec != 0, xw);
+    if (REV) reverse_regs(xw);                             // mirrored step index: the same causal arithmetic below
     const float* xv = xw + 1;                              // xv[j] = x[l0 - (W_max-1) + j]
-    float gw[4 * (CH + 1)];                                // dout[l0 .. l0 + STEPS + 4)
-    load_window<T, 0, CH>(gr, l0, a.L, a.vec != 0, gw);
+    float gw[4 * (CH + 1)];                                // dout[l0 .. l0 + STEPS + 4); REV: [l0 - 4 .. l0 + STEPS) mirrored
+    if (!REV) {
+      load_window<T, 0, CH>(gr, l0, a.L, a.vec != 0, gw);
+    } else {
+      load_window<T, 1, CH - 1>(gr, l0, a.L, a.vec != 0, gw);
+      reverse_regs(gw);
+    }
     float dy[STEPS + HR];                                  // dy[l0 .. l0 + STEPS + W-1)
 #pragma unroll
     for (int i = 0; i < STEPS + HR; ++i) {
@@ -194,32 +222,32 @@ __global__ void __launch_bounds__(kConvThreads) conv1d_bwd_kernel(const ConvArgs
       }
       dy[i] = g;
     }
+    float dxo[STEPS];
+#pragma unroll
+    for (int i = 0; i < STEPS; ++i) {
+      // dx[l] = sum_k w[k] * dy[l + (W-1) - k]
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kConvMaxW; ++k) {
+        const int kk = k - sh;
+        if (kk >= 0) acc = fmaf(w[kk], dy[i + (kConvMaxW - 1) - k], acc);
+      }
+      dxo[i] = acc;
+      // dw[k] += dy[l] * x[l - (W-1) + k],  dbias += dy[l]   (this thread owns steps l0 .. l0 + STEPS)
+      dbacc += dy[i];
+#pragma unroll
+      for (int k = 0; k < kConvMaxW; ++k) dwacc[k] = fmaf(dy[i], xv[i + k], dwacc[k]);
+    }
+    if (REV) reverse_regs(dxo);
 #pragma unroll
     for (int cch = 0; cch < CH; ++cch) {
-      float dxo[kConvVec];
-#pragma unroll
-      for (int ii = 0; ii < kConvVec; ++ii) {
-        const int i = 4 * cch + ii;
-        // dx[l] = sum_k w[k] * dy[l + (W-1) - k]
-        float acc = 0.f;
-#pragma unroll
-        for (int k = 0; k < kConvMaxW; ++k) {
-          const int kk = k - sh;
-          if (kk >= 0) acc = fmaf(w[kk], dy[i + (kConvMaxW - 1) - k], acc);
-        }
-        dxo[ii] = acc;
-        // dw[k] += dy[l] * x[l - (W-1) + k],  dbias += dy[l]   (this thread owns steps l0 .. l0 + STEPS)
-        dbacc += dy[i];
-#pragma unroll
-        for (int k = 0; k < kConvMaxW; ++k) dwacc[k] = fmaf(dy[i], xv[i + k], dwacc[k]);
-      }
       const long lc = l0 + 4 * cch;
       if (a.vec) {
-        if (lc < a.L) store4<T>(dxr + lc, dxo);
+        if (lc < a.L) store4<T>(dxr + lc, &dxo[4 * cch]);
       } else {
 #pragma unroll
         for (int ii = 0; ii < kConvVec; ++ii)
-          if (lc + ii < a.L) dxr[lc + ii] = Elem<T>::from_f(dxo[ii]);
+          if (lc + ii < a.L) dxr[lc + ii] = Elem<T>::from_f(dxo[4 * cch + ii]);
       }
     }
   }
@@ -291,9 +319,15 @@ int nz_causal_conv1d_fwd(const NzConv1dDesc* c, void* stream) {
   const long nblk_l = (a.L + nz::kConvThreads * steps - 1) / (nz::kConvThreads * steps);
   const unsigned grid = (unsigned)((long)a.batch * a.dim * nblk_l);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (c->dtype == NZ_F32) nz::conv1d_fwd_kernel<float><<<grid, nz::kConvThreads, 0, st>>>(a);
-  else if (c->dtype == NZ_BF16) nz::conv1d_fwd_kernel<__nv_bfloat16><<<grid, nz::kConvThreads, 0, st>>>(a);
-  else nz::conv1d_fwd_kernel<__half><<<grid, nz::kConvThreads, 0, st>>>(a);
+  if (c->reverse) {
+    if (c->dtype == NZ_F32) nz::conv1d_fwd_kernel<float, true><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else if (c->dtype == NZ_BF16) nz::conv1d_fwd_kernel<__nv_bfloat16, true><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else nz::conv1d_fwd_kernel<__half, true><<<grid, nz::kConvThreads, 0, st>>>(a);
+  } else {
+    if (c->dtype == NZ_F32) nz::conv1d_fwd_kernel<float, false><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else if (c->dtype == NZ_BF16) nz::conv1d_fwd_kernel<__nv_bfloat16, false><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else nz::conv1d_fwd_kernel<__half, false><<<grid, nz::kConvThreads, 0, st>>>(a);
+  }
   nz::count_launch(1);
   return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
 }
@@ -306,9 +340,15 @@ int nz_causal_conv1d_bwd(const NzConv1dDesc* c, void* stream) {
   const long nblk_l = (a.L + nz::kConvThreads * steps - 1) / (nz::kConvThreads * steps);
   const unsigned grid = (unsigned)((long)a.batch * a.dim * nblk_l);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (c->dtype == NZ_F32) nz::conv1d_bwd_kernel<float><<<grid, nz::kConvThreads, 0, st>>>(a);
-  else if (c->dtype == NZ_BF16) nz::conv1d_bwd_kernel<__nv_bfloat16><<<grid, nz::kConvThreads, 0, st>>>(a);
-  else nz::conv1d_bwd_kernel<__half><<<grid, nz::kConvThreads, 0, st>>>(a);
+  if (c->reverse) {
+    if (c->dtype == NZ_F32) nz::conv1d_bwd_kernel<float, true><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else if (c->dtype == NZ_BF16) nz::conv1d_bwd_kernel<__nv_bfloat16, true><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else nz::conv1d_bwd_kernel<__half, true><<<grid, nz::kConvThreads, 0, st>>>(a);
+  } else {
+    if (c->dtype == NZ_F32) nz::conv1d_bwd_kernel<float, false><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else if (c->dtype == NZ_BF16) nz::conv1d_bwd_kernel<__nv_bfloat16, false><<<grid, nz::kConvThreads, 0, st>>>(a);
+    else nz::conv1d_bwd_kernel<__half, false><<<grid, nz::kConvThreads, 0, st>>>(a);
+  }
   nz::count_launch(1);
   return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
 }

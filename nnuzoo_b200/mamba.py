@@ -9,11 +9,13 @@ parameter sets, which the reference creates unconditionally (:135-181).
   bimamba_type "none": mamba_inner_fn      = conv1d + SiLU -> x_proj -> dt_proj -> scan(z gate) -> out_proj
                "v2"  : out + flip(out_b)   (:250-281)
                "v3"  : out + flip(out_b) + un-interleave(out_s)   (:213-249, SegMamba's tri-directional block)
-The scan is ``nnuzoo_b200.selective_scan_fn`` (K = 1 group, B/C (b, 1, N, L), z gate, delta_softplus,
-bias = dt_proj.bias -- exactly the call of MambaInnerFnNoOutProj.forward,
-selective_scan_interface.py:159-226).  The depthwise causal conv + SiLU is ``nnuzoo_b200.causal_conv1d_fn``
-(csrc/conv1d_kernels.cu, widths <= 4; wider kernels fall back to cuDNN).  The incremental ``step`` / inference cache
-(:359-446) is not used by nnUZoo and is not implemented.
+Each direction is ONE autograd node, ``nnuzoo_b200.mamba_inner.MambaInnerFn`` (conv -> x_proj -> dt_proj -> scan with
+conv / delta recomputed in the backward, everything L-contiguous, B / C read as strided views: the reference's
+MambaInnerFn(NoOutProj), selective_scan_interface.py:159-434).  The ``_b`` direction runs over the UN-flipped xz
+(anti-causal convolution + reversed-walk scan), so ``xz.flip([-1])`` / ``out_b.flip([-1])`` (:251, :262) are never
+materialised; ``reverse=True`` on the module does the same for a whole block (MambaND's reversed layers,
+mamba_nd2net.py:638-656).  Convolutions wider than 4 taps take the op-by-op path around cuDNN.  The incremental
+``step`` / inference cache (:359-446) is not used by nnUZoo and is not implemented.
 """
 from __future__ import annotations
 
@@ -24,6 +26,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .causal_conv1d import causal_conv1d_fn
+from .mamba_inner import mamba_inner_fn, mamba_inner_fn_no_out_proj
 from .selective_scan_interface import selective_scan_fn
 
 
@@ -92,7 +95,13 @@ class Mamba(nn.Module):
         self.out_proj = nn.Linear(self.d_inner, self.d_model, bias=bias, **factory_kwargs)
 
     # what MambaInnerFnNoOutProj.forward computes (selective_scan_interface.py:159-226)
-    def _inner(self, xz, conv1d, x_proj, dt_proj, A_log, D):
+    def _inner(self, xz, conv1d, x_proj, dt_proj, A_log, D, reverse=False):
+        if self.d_conv <= 4 and self.use_fast_path:
+            return mamba_inner_fn_no_out_proj(xz, conv1d.weight, conv1d.bias, x_proj.weight, dt_proj.weight,
+                                              -torch.exp(A_log.float()), None, None, D.float(),
+                                              delta_bias=dt_proj.bias.float(), delta_softplus=True, reverse=reverse)
+        if reverse:
+            return self._inner(xz.flip([-1]), conv1d, x_proj, dt_proj, A_log, D).flip([-1])
         L = xz.shape[-1]
         x, z = xz.chunk(2, dim=1)
         if self.d_conv <= 4:   # causal depthwise conv + SiLU in one kernel (mamba_simple.py:319-324)
@@ -108,16 +117,30 @@ class Mamba(nn.Module):
         return selective_scan_fn(x, delta.contiguous(), A, B, C, D.float(), z=z,
                                  delta_bias=dt_proj.bias.float(), delta_softplus=True)
 
-    def forward(self, hidden_states, inference_params=None):
-        """hidden_states: (B, L, D) -> same shape (mamba_simple.py:191-357)."""
+    def forward(self, hidden_states, inference_params=None, *, reverse=False):
+        """hidden_states: (B, L, D) -> same shape (mamba_simple.py:191-357).
+
+        ``reverse=True`` (keyword-only extension): ``self(hidden_states.flip(1)).flip(1)`` by addressing -- every
+        per-token op commutes with the flip, the convolution runs anti-causally and the scan walks backwards."""
         if inference_params is not None:
             raise NotImplementedError("the incremental-decoding cache is not used by nnUZoo and not implemented")
         batch, seqlen, _ = hidden_states.shape
-        xz = self.in_proj(hidden_states).transpose(1, 2)                      # (b, 2*d_inner, l)  (:205-212)
-        out = self._inner(xz, self.conv1d, self.x_proj, self.dt_proj, self.A_log, self.D)
+        if reverse and self.bimamba_type != "none":
+            return self.forward(hidden_states.flip(1)).flip(1)
+        # (b, 2*d_inner, l) with l innermost straight out of the GEMM (:205-212): no transposed copy
+        xz = torch.matmul(self.in_proj.weight, hidden_states.transpose(1, 2))
+        if self.in_proj.bias is not None:
+            xz = xz + self.in_proj.bias.to(xz.dtype).unsqueeze(-1)
+        if self.bimamba_type == "none" and self.d_conv <= 4 and self.use_fast_path:   # (:299-313)
+            return mamba_inner_fn(xz, self.conv1d.weight, self.conv1d.bias, self.x_proj.weight, self.dt_proj.weight,
+                                  self.out_proj.weight, self.out_proj.bias, -torch.exp(self.A_log.float()), None, None,
+                                  self.D.float(), delta_bias=self.dt_proj.bias.float(), delta_softplus=True,
+                                  reverse=reverse)
+        out = self._inner(xz, self.conv1d, self.x_proj, self.dt_proj, self.A_log, self.D, reverse=reverse)
         if self.bimamba_type in ("v2", "v3"):
-            out_b = self._inner(xz.flip([-1]), self.conv1d_b, self.x_proj_b, self.dt_proj_b, self.A_b_log, self.D_b)
-            out = out + out_b.flip([-1])
+            # the backward direction over the un-flipped xz; its result is already un-flipped (:250-281)
+            out = out + self._inner(xz, self.conv1d_b, self.x_proj_b, self.dt_proj_b, self.A_b_log, self.D_b,
+                                    reverse=True)
         if self.bimamba_type == "v3":
             if seqlen % self.nslices:
                 raise ValueError("bimamba v3 needs seqlen to be a multiple of nslices")

@@ -53,3 +53,37 @@ def test_causal_conv1d_matches_oracle(case):
     assert rel_err(wd.grad.cpu().numpy(), rg["dw"]) < max(tol, 1e-4)
     if b is not None:
         assert rel_err(bd.grad.cpu().numpy(), rg["dbias"]) < max(tol, 1e-4)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_reverse_conv1d_is_the_flipped_convolution(case):
+    """reverse=True == causal_conv1d_fn(x.flip(-1)).flip(-1) (mamba_simple.py:250-262) without the flipped copies:
+    checked against the same oracle applied to the flipped sequence."""
+    from nnuzoo_b200 import causal_conv1d_fn
+    from oracle import conv_oracle
+    batch, dim, L, W, dt, has_bias, silu, view = case
+    dtype = getattr(torch, dt)
+    g = torch.Generator().manual_seed(7 + hash(case) % 1000)
+    full = torch.randn(batch, 2 * dim, L, generator=g).to(dtype)
+    w = torch.randn(dim, W, generator=g)
+    b = torch.randn(dim, generator=g) if has_bias else None
+    go = torch.randn(batch, dim, L, generator=g).to(dtype)
+    dev = torch.device("cuda:0")
+    fd = full.to(dev).requires_grad_(True)
+    xd = fd[:, :dim] if view else fd[:, :dim].contiguous()
+    wd = w.to(dev).requires_grad_(True)
+    bd = None if b is None else b.to(dev).requires_grad_(True)
+    out = causal_conv1d_fn(xd, wd, bd, "silu" if silu else None, reverse=True)
+    out.backward(go.to(dev))
+    torch.cuda.synchronize()
+    xs = np.ascontiguousarray(full[:, :dim].float().numpy()[..., ::-1])
+    gs = np.ascontiguousarray(go.float().numpy()[..., ::-1])
+    bn = None if b is None else b.numpy()
+    ref = conv_oracle.causal_conv1d_oracle(xs, w.numpy(), bn, silu)[..., ::-1]
+    rg = conv_oracle.causal_conv1d_oracle_bwd(xs, w.numpy(), bn, gs, silu)
+    tol = 1e-5 if dt == "float32" else 2e-2
+    assert rel_err(out.detach().float().cpu().numpy(), ref) < tol
+    assert rel_err(fd.grad[:, :dim].float().cpu().numpy(), rg["dx"][..., ::-1]) < tol
+    assert rel_err(wd.grad.cpu().numpy(), rg["dw"]) < max(tol, 1e-4)
+    if b is not None:
+        assert rel_err(bd.grad.cpu().numpy(), rg["dbias"]) < max(tol, 1e-4)

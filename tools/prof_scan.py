@@ -16,9 +16,7 @@ from nnuzoo_b200 import _native  # noqa: E402
 from nnuzoo_b200._native import NzScanDesc  # noqa: E402
 
 
-def main():
-    batch, kd, L = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (12, 128, 65536)
-    iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+def run(batch, kd, L, iters=3, quiet=False):
     G, N = 4, 16
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
@@ -69,7 +67,8 @@ def main():
         d0.xf = p(xf)
     wsb = max(int(lib.nz_scan_workspace_bytes_bwd(ctypes.byref(d0))), int(lib.nz_scan_workspace_bytes_cp(ctypes.byref(d0))))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-    print(f"fine checkpoints: {nfine} bytes, workspace {wsb} bytes")
+    if not quiet:
+        print(f"fine checkpoints: {nfine} bytes, workspace {wsb} bytes")
 
     E, S = rows, bc
     tf = tb = 0.0
@@ -91,9 +90,20 @@ def main():
             tf += e[0].elapsed_time(e[1])
             tb += e[1].elapsed_time(e[2])
     tf, tb = tf / iters, tb / iters
+    if quiet:
+        return tf, tb
     print(f"shape b={batch} kd={kd} L={L}: fwd {tf:.3f} ms ({4 * (3 * E + 2 * S) / tf / 1e6:.0f} GB/s)  "
           f"bwd {tb:.3f} ms ({4 * (5 * E + 4 * S) / tb / 1e6:.0f} GB/s)  "
           f"clk/elt/SM fwd {tf * 1e-3 * 148 * 1.965e9 / E:.2f} bwd {tb * 1e-3 * 148 * 1.965e9 / E:.2f}")
+
+
+    return tf, tb
+
+
+def main():
+    batch, kd, L = (int(a) for a in sys.argv[1:4]) if len(sys.argv) >= 4 else (12, 128, 65536)
+    iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+    run(batch, kd, L, iters)
 
 
 if __name__ == "__main__":
