@@ -543,6 +543,107 @@ def configs_run(dev, stream, peak):
                      "fwd_bwd_us": _median_ms(f3, stream, 50, 10) * 1e3, "our_launches_fwd_bwd": per_call})
     res["cfg3"] = {"what": "BASELINE configs[3] (MambaND2Net) token counts: microseconds per selective_scan_fn call "
                            "(Python wrapper + allocations + launches), fp32, z gate", "calls": rows}
+    del lv, g3
+    torch.cuda.empty_cache()
+    # ---- cfg2 as a config, not a shape: one ResMambaBlock (lm2net.py:107-176) of the stage-1 LightM-UNet level ----
+    try:
+        res["cfg2"]["block"] = _resmamba_block_run(dev, stream)
+    except Exception as e:  # noqa: BLE001  (a side measurement must not take the headline line down)
+        res["cfg2"]["block"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+    # ---- cfg3 as a config: the MambaNDCore block stack (mamba_nd2net.py:725-1001) ----
+    try:
+        res["cfg3"]["core"] = _mamba_nd_core_run(dev, stream)
+    except Exception as e:  # noqa: BLE001
+        res["cfg3"]["core"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.empty_cache()
+    return res
+
+
+def _resmamba_block_run(dev, stream):
+    """BASELINE configs[2]: ResMambaBlock(spatial_dims=3, in_channels=32, GroupNorm(8)) on a (2, 32, 128, 128, 128)
+    feature map under bf16 autocast, forward + backward, for the three axis orders LM2Net cycles through
+    (lm2net.py:286-315).  Each block runs two MambaLayers = two (2, 64, 2 097 152) scans with z gate."""
+    import torch
+
+    from nnuzoo_b200 import _native
+    from nnuzoo_b200.mamba_nd import ResMambaBlock
+    torch.manual_seed(11)
+    x = torch.randn(2, 32, 128, 128, 128, device=dev, requires_grad=True)
+    out = {"shape": "x (2, 32, 128, 128, 128), bf16 autocast, ResMambaBlock fwd+bwd (2 MambaLayers, d_inner 64, "
+                    "L = 2 097 152 each)", "orders": {}}
+    for order in ("d h w", "d w h", "w h d"):
+        blk = ResMambaBlock(3, 32, norm=("GROUP", {"num_groups": 8}), order=order).to(dev)
+
+        def f():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = blk(x)
+            y.float().square().mean().backward()
+            x.grad = None
+            blk.zero_grad(set_to_none=True)
+
+        n0 = _native.launch_count()
+        f()
+        launches = _native.launch_count() - n0
+        out["orders"][order] = {"fwd_bwd_ms": _median_ms(f, stream, 3, 1), "our_launches": launches}
+        del blk
+        torch.cuda.empty_cache()
+    out["timing"] = "median of 3 after 2 warm-ups, CUDA events, whole block (GSC convolutions / norms are library kernels)"
+    return out
+
+
+def _mamba_nd_core_run(dev, stream):
+    """BASELINE configs[3]: the MambaNDCore block stack at MambaND2Net's token grid -- 7 Blocks, d_model 96, tokens
+    (6, 10, 10), batch 2, three orders x reversed odd layers (mamba_nd2net.py:960-1001) -- eager and as a replayed CUDA
+    graph (the path is launch-bound: L = 600)."""
+    import torch
+
+    from nnuzoo_b200 import _native
+    from nnuzoo_b200.mamba_nd import MambaNDCore
+    torch.manual_seed(12)
+    nl = 7
+    core = MambaNDCore(spatial_dims=3, img_size=(12, 20, 20), patch_size=(2, 2, 2), in_channels=1, embed_dims=96,
+                       num_layers=nl, fused_add_norm=False, final_norm=False).to(dev)
+    shape = (6, 10, 10)
+    x = torch.randn(2, 600, 96, device=dev, requires_grad=True)
+    gy = torch.randn(2, 600, 96, device=dev)
+
+    def fwd():
+        with torch.no_grad():
+            core.forward_tokens(x, shape)
+
+    def both():
+        y, _ = core.forward_tokens(x, shape)
+        y.backward(gy)
+        x.grad = None
+        core.zero_grad(set_to_none=True)
+
+    n0 = _native.launch_count()
+    both()
+    launches = _native.launch_count() - n0
+    res = {"shape": "tokens (2, 600, 96) = grid (6, 10, 10), 7 Blocks, d_inner 192, fp32",
+           "fwd_us_per_block": _median_ms(fwd, stream, 30, 5) * 1e3 / nl,
+           "fwd_bwd_us_per_block": _median_ms(both, stream, 30, 5) * 1e3 / nl,
+           "our_launches_per_block_fwd_bwd": launches / nl}
+    # replayed CUDA graph of forward + backward (static input / gradient buffers)
+    try:
+        params = [q for q in core.parameters()]
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                y, _ = core.forward_tokens(x, shape)
+                torch.autograd.grad(y, [x] + params, gy, allow_unused=True)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            y, _ = core.forward_tokens(x, shape)
+            grads = torch.autograd.grad(y, [x] + params, gy, allow_unused=True)
+        _ = grads
+        t = _median_ms(graph.replay, torch.cuda.current_stream(dev), 50, 10)
+        res["graph_fwd_bwd_us_per_block"] = t * 1e3 / nl
+    except Exception as e:  # noqa: BLE001
+        res["graph_error"] = f"{type(e).__name__}: {e}"[:300]
     return res
 
 

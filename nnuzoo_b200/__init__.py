@@ -6,6 +6,9 @@ Public surface (mirrors the reference's operator / module interface for this one
   SS2D, SSND                           <- m2net.py:39-225; ssnd2net.py:73-318
   Mamba                                <- seg_mamba/mamba_simple.py:37-357 (1-D nets; uni / bi / tri-directional)
   causal_conv1d_fn                     <- mamba_simple.py:316-324 (the block's depthwise causal conv + SiLU)
+  mamba_inner_fn(_no_out_proj)         <- selective_scan_interface.py:159-434, :609-628 (conv -> projections -> scan, one node)
+  MambaLayer, ResMambaBlock, nd_mamba_order, Block, create_block, MambaNDCore (nnuzoo_b200.mamba_nd)
+                                       <- lm2net.py:64-176, mamba_nd2net.py:565-722, :725-1001 (callers of the 1-D path)
   M2Net, get_m2net (nnuzoo_b200.m2net) <- m2net.py:805-971, :1187-1208 (SS2D^2-Net, the config-2 network)
   Trainer (nnuzoo_b200.train)          <- nnUNetTrainer.py:1112-1144 + nnUNetTrainerM2Net.py (DDP training step)
   SlidingWindowPredictor (.predict)    <- inference/predict_from_raw_data.py:515-690 (rank-sharded tiles)
@@ -20,6 +23,8 @@ from .cross_scan import cross_merge, cross_scan  # noqa: F401
 from .ss2d import SS2D, SSND  # noqa: F401
 from .causal_conv1d import causal_conv1d_fn  # noqa: F401
 from .mamba import Mamba  # noqa: F401
+from .mamba_inner import mamba_inner_fn, mamba_inner_fn_no_out_proj  # noqa: F401
+from .mamba_nd import Block, MambaLayer, MambaNDCore, ResMambaBlock, create_block, nd_mamba_order  # noqa: F401
 from .norm import LayerNorm, layer_norm  # noqa: F401
 from .proj import grouped_proj, proj_wgrad  # noqa: F401
 from .dwconv import dwconv3x3_silu  # noqa: F401
@@ -27,4 +32,6 @@ from .fused import ss2d_core  # noqa: F401
 from .m2net import M2Net, get_m2net  # noqa: F401
 
 __all__ = ["selective_scan_fn", "SelectiveScanFn", "cross_scan", "cross_merge", "SS2D", "SSND", "Mamba", "causal_conv1d_fn",
+           "mamba_inner_fn", "mamba_inner_fn_no_out_proj", "MambaLayer", "ResMambaBlock", "nd_mamba_order", "Block",
+           "create_block", "MambaNDCore",
            "LayerNorm", "layer_norm", "grouped_proj", "proj_wgrad", "dwconv3x3_silu", "ss2d_core", "M2Net", "get_m2net"]

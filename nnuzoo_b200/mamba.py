@@ -33,7 +33,8 @@ from .selective_scan_interface import selective_scan_fn
 class Mamba(nn.Module):
     def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
                  dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, conv_bias=True, bias=False,
-                 use_fast_path=True, layer_idx=None, device=None, dtype=None, bimamba_type="none", nslices=5):
+                 use_fast_path=True, layer_idx=None, device=None, dtype=None, bimamba_type="none", nslices=5,
+                 extra_directions=True):
         factory_kwargs = {"device": device, "dtype": dtype}
         super().__init__()
         self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
@@ -86,12 +87,15 @@ class Mamba(nn.Module):
             return p
 
         self.A_log, self.D = s4d_real(), skip()
-        self.A_b_log = s4d_real()          # backward direction (:130-154)
-        direction("_b")
-        self.D_b = skip()
-        self.A_s_log = s4d_real()          # slice-interleaved direction (:158-181)
-        direction("_s")
-        self.D_s = skip()
+        # extra_directions=False gives the parameter set of upstream ``mamba_ssm.Mamba`` (one direction), which is what
+        # lm2net.py:14 / mamba_nd2net.py:26 import; the vendored block creates the other two unconditionally
+        if extra_directions or bimamba_type != "none":
+            self.A_b_log = s4d_real()          # backward direction (:130-154)
+            direction("_b")
+            self.D_b = skip()
+            self.A_s_log = s4d_real()          # slice-interleaved direction (:158-181)
+            direction("_s")
+            self.D_s = skip()
         self.out_proj = nn.Linear(self.d_inner, self.d_model, bias=bias, **factory_kwargs)
 
     # what MambaInnerFnNoOutProj.forward computes (selective_scan_interface.py:159-226)

@@ -240,6 +240,71 @@ def gen_mamba(manifest):
         manifest["module"][name] = dict(x_shape=list(xshape), y_abs_mean=float(y.abs().mean()), bimamba_type=kind)
 
 
+def _record(mod, x, fwd, name, manifest, extra=None):
+    y = fwd(mod, x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    rec = {"x": _np(x), "y": _np(y), "gy": _np(gy), "gx": _np(x.grad)}
+    for k, v in mod.state_dict().items():
+        rec["sd_" + k] = _np(v)
+    for k, p in mod.named_parameters():
+        rec["gp_" + k] = _np(p.grad) if p.grad is not None else np.zeros(tuple(p.shape), np.float32)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **rec)
+    manifest["module"][name] = dict(x_shape=list(x.shape), y_abs_mean=float(y.abs().mean()), **(extra or {}))
+
+
+def _perturb_mamba(mod):
+    with torch.no_grad():  # move the scan parameters off their symmetric init
+        for k, p in mod.named_parameters():
+            if k.endswith("A_log") or k.endswith(".D") or k == "D":
+                p.add_(0.1 * torch.randn_like(p))
+            if k.endswith("skip_scale"):
+                p.add_(0.3)
+
+
+def gen_shells(manifest):
+    """shell_*.npz: the callers of the 1-D path run by the reference itself -- MambaLayer / ResMambaBlock with its three
+    axis orders (lm2net.py:64-176), MambaND's Block for every order x direction and a 7-layer MambaNDCore
+    (mamba_nd2net.py:565-666, :725-1001; fused_add_norm=False, final_norm=False as MambaND2Net builds it, :1128-1147)."""
+    lm = ref_loader.lm2net()
+    nd = ref_loader.mamba_nd2net()
+    torch.manual_seed(700)
+    mod = lm.MambaLayer(input_dim=16, output_dim=24).eval()
+    _perturb_mamba(mod)
+    _record(mod, torch.randn(2, 16, 3, 4, 5, requires_grad=True), lambda m, x: m(x), "shell_mambalayer", manifest)
+    specs = {"shell_resmamba_dhw": (3, "d h w", (1, 16, 3, 4, 5)), "shell_resmamba_dwh": (3, "d w h", (1, 16, 3, 4, 5)),
+             "shell_resmamba_whd": (3, "w h d", (1, 16, 3, 4, 5)), "shell_resmamba_wh": (2, "w h", (2, 16, 5, 6))}
+    for i, (name, (sd, order, xs)) in enumerate(specs.items()):
+        torch.manual_seed(710 + i)
+        mod = lm.ResMambaBlock(sd, 16, norm=("GROUP", {"num_groups": 8}), order=order).eval()
+        _perturb_mamba(mod)
+        _record(mod, torch.randn(*xs, requires_grad=True), lambda m, x: m(x), name, manifest,
+                dict(order=order, spatial_dims=sd))
+    shape = (2, 3, 4)
+    for i, order in enumerate(("t h w", "t w h", "w h t")):
+        for rev in (False, True):
+            torch.manual_seed(730 + 2 * i + int(rev))
+            blk = nd.create_block(spatial_dims=3, d_model=16, ssm_cfg={"d_state": 16}, fused_add_norm=False,
+                                  residual_in_fp32=True, reverse=rev, drop_rate=0.0, drop_path_rate=0.0).eval()
+            _perturb_mamba(blk)
+            name = f"shell_ndblock_{order.replace(' ', '')}_{'rev' if rev else 'fwd'}"
+            _record(blk, torch.randn(2, 24, 16, requires_grad=True),
+                    lambda m, x, o=order: m(x, order=o, shape=shape, n_dim_pos=4), name, manifest,
+                    dict(order=order, reverse=rev, shape=list(shape)))
+    torch.manual_seed(750)
+    core = nd.MambaNDCore(spatial_dims=3, img_size=(4, 6, 6), patch_size=(2, 2, 2), in_channels=2, embed_dims=16,
+                          num_layers=7, fused_add_norm=False, final_norm=False, drop_rate=0.0, drop_path_rate=0.0).eval()
+    _perturb_mamba(core)
+    _record(core, torch.randn(2, 2, 4, 6, 6, requires_grad=True), lambda m, x: m(x)[0], "shell_ndcore", manifest,
+            dict(num_layers=7, patch_size=[2, 2, 2]))
+    torch.manual_seed(751)
+    core2 = nd.MambaNDCore(spatial_dims=2, img_size=(8, 8), patch_size=(2, 2), in_channels=1, embed_dims=16,
+                           num_layers=4, fused_add_norm=False, final_norm=False, drop_rate=0.0, drop_path_rate=0.0).eval()
+    _perturb_mamba(core2)
+    _record(core2, torch.randn(2, 1, 8, 8, requires_grad=True), lambda m, x: m(x)[0], "shell_ndcore2d", manifest,
+            dict(num_layers=4, patch_size=[2, 2]))
+
+
 M2NET_FULL_GRADS = ("stage1.vssm_encoder.layers.0.blocks.0.self_attention.A_logs",
                     "stage1.vssm_encoder.layers.0.blocks.0.self_attention.x_proj_weight",
                     "stage1d.vssm_decoder.stages.5.blocks.0.self_attention.dt_projs_bias",
@@ -288,6 +353,7 @@ def main():
     gen_module(manifest)
     gen_mamba(manifest)
     gen_m2net(manifest)
+    gen_shells(manifest)
     with open(os.path.join(GOLD, "MANIFEST.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
     print(json.dumps(manifest, indent=1, sort_keys=True))

@@ -120,6 +120,10 @@ def _install_stubs():
             super().__init__()
             assert conv_only, "only the conv_only form is stood in for"
             conv_t = {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}[spatial_dims]
+            if padding is None:  # monai: same_padding(kernel_size, dilation)
+                ks = (kernel_size,) * spatial_dims if isinstance(kernel_size, int) else tuple(kernel_size)
+                dl = (dilation,) * spatial_dims if isinstance(dilation, int) else tuple(dilation)
+                padding = tuple((k - 1) // 2 * d for k, d in zip(ks, dl))
             self.add_module("conv", conv_t(in_channels, out_channels, kernel_size, stride=strides,
                                            padding=padding, dilation=dilation, groups=groups, bias=bias))
 
@@ -127,6 +131,26 @@ def _install_stubs():
     import monai.networks.blocks.convolutions as mbc  # noqa: E402
 
     mbc.Convolution = Convolution
+
+    # --- monai factories the LightM-UNet blocks execute (lm2net.py:17-18, :130-132) ----------------
+    import monai.networks.layers.utils as mlu  # noqa: E402  (stub)
+
+    def get_norm_layer(name, spatial_dims=1, channels=1):
+        nm, args = (name, {}) if isinstance(name, str) else (name[0], dict(name[1]))
+        nm = nm.lower()
+        if nm == "group":
+            return nn.GroupNorm(num_channels=channels, **args)
+        if nm == "instance":
+            return {2: nn.InstanceNorm2d, 3: nn.InstanceNorm3d}[spatial_dims](channels, **args)
+        if nm == "batch":
+            return {2: nn.BatchNorm2d, 3: nn.BatchNorm3d}[spatial_dims](channels, **args)
+        raise NotImplementedError(name)
+
+    def get_act_layer(name):
+        nm, args = (name, {}) if isinstance(name, str) else (name[0], dict(name[1]))
+        return {"relu": nn.ReLU, "leakyrelu": nn.LeakyReLU, "gelu": nn.GELU}[nm.lower()](**args)
+
+    mlu.get_norm_layer, mlu.get_act_layer = get_norm_layer, get_act_layer
 
     import dynamic_network_architectures.initialization.weight_init as wi  # noqa: E402
 
@@ -216,6 +240,27 @@ def mamba_simple():
 
 def m2net():
     return load_file("ref_m2net", "nnunetv2/nets/m2net.py")
+
+
+def _bind_mamba():
+    """``from mamba_ssm import Mamba`` (lm2net.py:14, mamba_nd2net.py:26) := the reference's vendored block wired for the
+    CPU (mamba_simple() above); with bimamba_type "none" it is the same contract as upstream's."""
+    ms = mamba_simple()
+    import mamba_ssm  # noqa: E402  (stub)
+    mamba_ssm.Mamba = ms.Mamba
+    return ms
+
+
+def lm2net():
+    """LightM-UNet blocks (MambaLayer, GSC, ResMambaBlock): nnunetv2/nets/lm2net.py."""
+    _bind_mamba()
+    return load_file("ref_lm2net", "nnunetv2/nets/lm2net.py")
+
+
+def mamba_nd2net():
+    """MambaND blocks (Block, create_block, MambaNDCore): nnunetv2/nets/mamba_nd2net.py."""
+    _bind_mamba()
+    return load_file("ref_mamba_nd2net", "nnunetv2/nets/mamba_nd2net.py")
 
 
 def ssnd2net():
