@@ -539,8 +539,32 @@ def configs_run(dev, stream, peak):
         n0 = _native.launch_count()
         f3()
         per_call = _native.launch_count() - n0
-        rows.append({"shape": [2, Dm, L], "fwd_us": _median_ms(f3f, stream, 50, 10) * 1e3,
-                     "fwd_bwd_us": _median_ms(f3, stream, 50, 10) * 1e3, "our_launches_fwd_bwd": per_call})
+        row = {"shape": [2, Dm, L], "fwd_us": _median_ms(f3f, stream, 50, 10) * 1e3,
+               "fwd_bwd_us": _median_ms(f3, stream, 50, 10) * 1e3, "our_launches_fwd_bwd": per_call}
+        try:  # the same calls replayed from a CUDA graph: device time without the Python / allocator / launch overhead
+            for t in lv + [A, Dp, bias]:
+                t.grad = None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    f3f()
+                    o = selective_scan_fn(lv[0], lv[1], A, lv[2], lv[3], Dp, lv[4], bias, True)
+                    torch.autograd.grad(o, lv + [A, Dp, bias], g3)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf):
+                f3f()
+            with torch.cuda.graph(gb):
+                o = selective_scan_fn(lv[0], lv[1], A, lv[2], lv[3], Dp, lv[4], bias, True)
+                keep = torch.autograd.grad(o, lv + [A, Dp, bias], g3)
+            cur = torch.cuda.current_stream(dev)
+            row["graph_fwd_us"] = _median_ms(gf.replay, cur, 100, 20) * 1e3
+            row["graph_fwd_bwd_us"] = _median_ms(gb.replay, cur, 100, 20) * 1e3
+            del keep, gf, gb
+        except Exception as e:  # noqa: BLE001
+            row["graph_error"] = f"{type(e).__name__}: {e}"[:200]
+        rows.append(row)
     res["cfg3"] = {"what": "BASELINE configs[3] (MambaND2Net) token counts: microseconds per selective_scan_fn call "
                            "(Python wrapper + allocations + launches), fp32, z gate", "calls": rows}
     del lv, g3

@@ -15,6 +15,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/nnuzoo_b200.h"
 
@@ -149,12 +150,38 @@ __global__ void cross_merge_bwd_kernel(const float* __restrict__ dy, float* __re
 // association order, so still bit-identical to the reference expressions.
 constexpr int kCT = 32;
 
+// Direction slots of the (b, K, d, L) array a tiled pass touches; -1 = not written / read by this pass.
+//   copy / copy_flip : the row-major walk of the (H, W) matrix and its L-flip
+//   tr / tr_flip     : the column-major walk t(p) = w * H + h and its L-flip
+//   zero_a / zero_b  : slots this pass fills with zeros (the 3-D reference merge never reads directions 2 / 5)
+// The 3-D walks are the same two maps on re-factored matrices: "w z h" (ssnd2net.py:251) is the column-major walk of the
+// (Z*H) x W matrix, "h w z" (:252) of the Z x (H*W) matrix, and the reference's second un-permute of direction 1
+// (:295-296) of the H x (W*Z) matrix -- so every 3-D direction moves through the same 32 x 32 shared-memory tiles.
+struct Slots {
+  int K, copy, copy_flip, tr, tr_flip, zero_a, zero_b;
+  int accumulate;  // scan: add into tr / tr_flip instead of overwriting (fp32 only); merge: start from y instead of copy
+};
+
+template <typename T>
+__device__ __forceinline__ void put(T* p, T v, bool acc) { *p = v; (void)acc; }
+template <>
+__device__ __forceinline__ void put<uint32_t>(uint32_t* p, uint32_t v, bool acc) {
+  if (acc) {
+    float* f = reinterpret_cast<float*>(p);
+    *f = *f + __uint_as_float(v);
+  } else {
+    *p = v;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) cross_scan2d_tiled_kernel(const T* __restrict__ x, T* __restrict__ xs, long planes,
-                                                                 int dim, long H, long W, int tiles_w, int tiles_h) {
+                                                                 int dim, long H, long W, int tiles_w, int tiles_h,
+                                                                 const Slots sl) {
   __shared__ T tile[kCT][kCT + 1];
   const long L = H * W;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const bool acc = sl.accumulate != 0;
   for (long blk = blockIdx.x;; blk += gridDim.x) {
     const long plane = blk / ((long)tiles_w * tiles_h);
     const int tr = (int)(blk % ((long)tiles_w * tiles_h));
@@ -163,18 +190,23 @@ __global__ void __launch_bounds__(256) cross_scan2d_tiled_kernel(const T* __rest
     const long b = plane / dim;
     const int dd = (int)(plane % dim);
     const T* src = x + plane * L;
-    T* o0 = xs + ((b * 4 + 0) * dim + dd) * L;
-    T* o1 = xs + ((b * 4 + 1) * dim + dd) * L;
-    T* o2 = xs + ((b * 4 + 2) * dim + dd) * L;
-    T* o3 = xs + ((b * 4 + 3) * dim + dd) * L;
+    auto slot = [&](int k) { return k < 0 ? (T*)nullptr : xs + ((b * sl.K + k) * dim + dd) * L; };
+    T* o0 = slot(sl.copy);
+    T* o1 = slot(sl.tr);
+    T* o2 = slot(sl.copy_flip);
+    T* o3 = slot(sl.tr_flip);
+    T* z0 = slot(sl.zero_a);
+    T* z1 = slot(sl.zero_b);
 #pragma unroll
     for (int r = 0; r < kCT; r += 8) {
       const long h = h0 + ty + r, w = w0 + tx;
       if (h < H && w < W) {
         const T v = src[h * W + w];
         tile[ty + r][tx] = v;
-        o0[h * W + w] = v;
-        o2[L - 1 - (h * W + w)] = v;
+        if (o0) o0[h * W + w] = v;
+        if (o2) o2[L - 1 - (h * W + w)] = v;
+        if (z0) z0[h * W + w] = T(0);
+        if (z1) z1[h * W + w] = T(0);
       }
     }
     __syncthreads();
@@ -183,18 +215,20 @@ __global__ void __launch_bounds__(256) cross_scan2d_tiled_kernel(const T* __rest
       const long w = w0 + ty + r, h = h0 + tx;
       if (h < H && w < W) {
         const T v = tile[tx][ty + r];
-        o1[w * H + h] = v;
-        o3[L - 1 - (w * H + h)] = v;
+        if (o1) put<T>(o1 + (w * H + h), v, acc);
+        if (o3) put<T>(o3 + (L - 1 - (w * H + h)), v, acc);
       }
     }
     __syncthreads();
   }
 }
 
-// out_y (b, 4, d, L) -> y (b, d, L): ((y0[p] + y2[L-1-p]) + y1[t(p)]) + y3[L-1-t(p)], t(p) = w * H + h
+// out_y (b, K, d, L) -> y (b, d, L): ((start + tr[t(p)]) + tr_flip[L-1-t(p)]), t(p) = w * H + h, where
+// start = copy[p] + copy_flip[L-1-p], or y[p] itself when sl.accumulate (the second pass of the 3-D merge).  Separate
+// fp32 adds in the reference's left-to-right order (m2net.py:218, ssnd2net.py:298).
 __global__ void __launch_bounds__(256) cross_merge2d_tiled_kernel(const float* __restrict__ oy, float* __restrict__ y,
                                                                   long planes, int dim, long H, long W, int tiles_w,
-                                                                  int tiles_h) {
+                                                                  int tiles_h, const Slots sl) {
   __shared__ float t1[kCT][kCT + 1], t3[kCT][kCT + 1];
   const long L = H * W;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -205,10 +239,11 @@ __global__ void __launch_bounds__(256) cross_merge2d_tiled_kernel(const float* _
     const long h0 = (long)(tr / tiles_w) * kCT, w0 = (long)(tr % tiles_w) * kCT;
     const long b = plane / dim;
     const int dd = (int)(plane % dim);
-    const float* i0 = oy + ((b * 4 + 0) * dim + dd) * L;
-    const float* i1 = oy + ((b * 4 + 1) * dim + dd) * L;
-    const float* i2 = oy + ((b * 4 + 2) * dim + dd) * L;
-    const float* i3 = oy + ((b * 4 + 3) * dim + dd) * L;
+    auto slot = [&](int k) { return oy + ((b * sl.K + (k < 0 ? 0 : k)) * dim + dd) * L; };
+    const float* i0 = slot(sl.copy);
+    const float* i1 = slot(sl.tr);
+    const float* i2 = slot(sl.copy_flip);
+    const float* i3 = slot(sl.tr_flip);
 #pragma unroll
     for (int r = 0; r < kCT; r += 8) {  // column-major directions: contiguous in h
       const long w = w0 + ty + r, h = h0 + tx;
@@ -223,8 +258,13 @@ __global__ void __launch_bounds__(256) cross_merge2d_tiled_kernel(const float* _
       const long h = h0 + ty + r, w = w0 + tx;
       if (h < H && w < W) {
         const long p = h * W + w;
-        float acc = i0[p];
-        acc = acc + i2[L - 1 - p];
+        float acc;
+        if (sl.accumulate) {
+          acc = y[plane * L + p];
+        } else {
+          acc = i0[p];
+          acc = acc + i2[L - 1 - p];
+        }
         acc = acc + t1[tx][ty + r];
         acc = acc + t3[tx][ty + r];
         y[plane * L + p] = acc;
@@ -362,16 +402,26 @@ int nz_cross_scan(const void* x, void* xs, int32_t dtype, int32_t batch, int32_t
   int grid;
   const int threads = nz::launch_cfg(rows * 2 * nspatial * s.L, &grid);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (nspatial == 2 && (dtype == NZ_F32 || dtype == NZ_BF16 || dtype == NZ_F16)) {
-    int tw, th;
-    const int g = nz::tiled_grid(rows, s.H, s.W, &tw, &th);
-    if (dtype == NZ_F32)
-      nz::cross_scan2d_tiled_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(x),
-                                                                 static_cast<uint32_t*>(xs), rows, dim, s.H, s.W, tw, th);
-    else
-      nz::cross_scan2d_tiled_kernel<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(x),
-                                                                 static_cast<uint16_t*>(xs), rows, dim, s.H, s.W, tw, th);
-    nz::count_launch(1);
+  if ((dtype == NZ_F32 || dtype == NZ_BF16 || dtype == NZ_F16) && !getenv("NZ_CROSS_GENERIC")) {
+    // 2-D: one tiled pass.  3-D: two -- the (Z*H) x W matrix gives k0, k1 "w z h" and their flips k3, k4, the
+    // Z x (H*W) matrix gives k2 "h w z" and k5 (see Slots).
+    auto pass = [&](long Hm, long Wm, const nz::Slots& sl) {
+      int tw, th;
+      const int g = nz::tiled_grid(rows, Hm, Wm, &tw, &th);
+      if (dtype == NZ_F32)
+        nz::cross_scan2d_tiled_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(x),
+                                                                   static_cast<uint32_t*>(xs), rows, dim, Hm, Wm, tw, th, sl);
+      else
+        nz::cross_scan2d_tiled_kernel<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(x),
+                                                                   static_cast<uint16_t*>(xs), rows, dim, Hm, Wm, tw, th, sl);
+      nz::count_launch(1);
+    };
+    if (nspatial == 2) {
+      pass(s.H, s.W, nz::Slots{4, 0, 2, 1, 3, -1, -1, 0});
+    } else {
+      pass(s.Z * s.H, s.W, nz::Slots{6, 0, 3, 1, 4, -1, -1, 0});
+      pass(s.Z, s.H * s.W, nz::Slots{6, -1, -1, 2, 5, -1, -1, 0});
+    }
     return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
   }
   if (dtype == NZ_F32)
@@ -391,12 +441,24 @@ int nz_cross_merge(const float* out_y, float* y, int32_t batch, int32_t dim, int
   nz::Dims s;
   if (!out_y || !y || batch < 1 || dim < 1 || !nz::make_dims(nspatial, spatial, &s)) return NZ_EINVAL;
   const long rows = (long)batch * dim;
-  if (nspatial == 2) {
-    int tw, th;
-    const int g = nz::tiled_grid(rows, s.H, s.W, &tw, &th);
-    nz::cross_merge2d_tiled_kernel<<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out_y, y, rows, dim, s.H, s.W,
-                                                                                         tw, th);
-    nz::count_launch(1);
+  if (!getenv("NZ_CROSS_GENERIC")) {
+    auto pass = [&](long Hm, long Wm, const nz::Slots& sl) {
+      int tw, th;
+      const int g = nz::tiled_grid(rows, Hm, Wm, &tw, &th);
+      nz::cross_merge2d_tiled_kernel<<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(out_y, y, rows, dim, Hm, Wm,
+                                                                                           tw, th, sl);
+      nz::count_launch(1);
+    };
+    if (nspatial == 2) {
+      pass(s.H, s.W, nz::Slots{4, 0, 2, 1, 3, -1, -1, 0});
+    } else {
+      // ((((y0 + inv0) + wzh) + inv_wzh) + third) + inv_third  (ssnd2net.py:298): the first four terms on the
+      // (Z*H) x W matrix, the last two added onto y by a second pass -- reference mode reads direction 1 / 4 again
+      // through the H x (W*Z) matrix (:295-296), "fixed" mode direction 2 / 5 through the Z x (H*W) one
+      pass(s.Z * s.H, s.W, nz::Slots{6, 0, 3, 1, 4, -1, -1, 0});
+      if (mode == 0) pass(s.H, s.W * s.Z, nz::Slots{6, -1, -1, 1, 4, -1, -1, 1});
+      else pass(s.Z, s.H * s.W, nz::Slots{6, -1, -1, 2, 5, -1, -1, 1});
+    }
     return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
   }
   int grid;
@@ -411,12 +473,24 @@ int nz_cross_merge_bwd(const float* dy, float* d_out_y, int32_t batch, int32_t d
   nz::Dims s;
   if (!dy || !d_out_y || batch < 1 || dim < 1 || !nz::make_dims(nspatial, spatial, &s)) return NZ_EINVAL;
   const long rows = (long)batch * dim;
-  if (nspatial == 2) {  // in 2-D the adjoint of the merge is the scan permutation applied to dy (fp32)
-    int tw, th;
-    const int g = nz::tiled_grid(rows, s.H, s.W, &tw, &th);
-    nz::cross_scan2d_tiled_kernel<uint32_t><<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const uint32_t*>(dy), reinterpret_cast<uint32_t*>(d_out_y), rows, dim, s.H, s.W, tw, th);
-    nz::count_launch(1);
+  if (!getenv("NZ_CROSS_GENERIC")) {  // the adjoint of the merge is the scan permutation applied to dy (fp32)
+    auto pass = [&](long Hm, long Wm, const nz::Slots& sl) {
+      int tw, th;
+      const int g = nz::tiled_grid(rows, Hm, Wm, &tw, &th);
+      nz::cross_scan2d_tiled_kernel<uint32_t><<<g, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+          reinterpret_cast<const uint32_t*>(dy), reinterpret_cast<uint32_t*>(d_out_y), rows, dim, Hm, Wm, tw, th, sl);
+      nz::count_launch(1);
+    };
+    if (nspatial == 2) {
+      pass(s.H, s.W, nz::Slots{4, 0, 2, 1, 3, -1, -1, 0});
+    } else if (mode == 0) {
+      // reference merge: directions 1 / 4 receive dy twice (two different un-permutes), 2 / 5 nothing
+      pass(s.Z * s.H, s.W, nz::Slots{6, 0, 3, 1, 4, 2, 5, 0});
+      pass(s.H, s.W * s.Z, nz::Slots{6, -1, -1, 1, 4, -1, -1, 1});
+    } else {
+      pass(s.Z * s.H, s.W, nz::Slots{6, 0, 3, 1, 4, -1, -1, 0});
+      pass(s.Z, s.H * s.W, nz::Slots{6, -1, -1, 2, 5, -1, -1, 0});
+    }
     return cudaGetLastError() == cudaSuccess ? NZ_OK : NZ_ECUDA;
   }
   int grid;
