@@ -301,6 +301,28 @@ int nz_ss2d_epilogue_bwd_folded(const void* dout, const float* y_merged, const f
                                 int32_t batch, int32_t D, int32_t H, int32_t W, void* stream);
 
 /*
+ * Sliding-window accumulate: the per-tile arithmetic of the predictor's inner loop as one launch --
+ *   mirror average   prediction = net(x); prediction += flip(net(flip(x, c)), c) ...; prediction /= passes
+ *                                                           (inference/predict_from_raw_data.py:549-565)
+ *   accumulate       prediction = prediction.to(results dtype) * gaussian; predicted_logits[sl] += prediction;
+ *                    n_predictions[sl[1:]] += gaussian                                        (:617-623)
+ * with a rounding after every one of those steps, so the accumulators are bit-identical to the PyTorch expressions.
+ *   pred     (nmirror * ntiles, heads, t0, t1, t2) contiguous in pred_dtype: pass m of tile t at index m * ntiles + t;
+ *            pass 0 is un-mirrored, pass m was computed on the tile flipped along the axes in mirror_masks[m] (bit a =
+ *            tile axis a) and is read back through the same flip.  nmirror is 1, 2, 4 or 8.
+ *   gaussian (t0, t1, t2) in res_dtype (all ones when the reference's use_gaussian is off)
+ *   logits   (heads, v0, v1, v2), n_pred (v0, v1, v2) in res_dtype, updated in place
+ *   offsets  (ntiles, 3) HOST array: origin of each tile in the volume.  A 2-D tile of a 3-D volume has t0 = 1.
+ * The tiles of ONE call must not overlap in the volume (each element has one owner thread); overlapping tiles go in
+ * separate calls, which the stream orders.  ntiles <= NZ_SW_MAX_TILES.
+ */
+#define NZ_SW_MAX_TILES 32
+#define NZ_SW_MAX_MIRRORS 8
+int nz_sw_accumulate(const void* pred, int32_t pred_dtype, int32_t nmirror, const int32_t* mirror_masks, int32_t ntiles,
+                     int32_t heads, const int64_t* tile, const void* gaussian, int32_t res_dtype, void* logits,
+                     void* n_pred, const int64_t* vol, const int64_t* offsets, void* stream);
+
+/*
  * Host-buffer entry points (what a non-PyTorch caller of the reference's operator would bind):
  * every pointer in `desc` is a HOST pointer, strides as above; the call stages host -> device,
  * runs nz_scan_fwd (and nz_scan_bwd when desc->dout != NULL) and copies the results back,

@@ -131,6 +131,9 @@ def lib():
                 for name in ("nz_cross_scan_pair", "nz_cross_merge_pair"):
                     getattr(L, name).argtypes = [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]
                     getattr(L, name).restype = ctypes.c_int
+                L.nz_sw_accumulate.argtypes = [_vp, _i32, _i32, ctypes.POINTER(_i32), _i32, _i32, ctypes.POINTER(_i64), _vp,
+                                               _i32, _vp, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), _vp]
+                L.nz_sw_accumulate.restype = ctypes.c_int
                 L.nz_sizeof_conv1d_desc.restype = _i64
                 if L.nz_sizeof_conv1d_desc() != ctypes.sizeof(NzConv1dDesc):
                     raise NativeLibraryError("NzConv1dDesc layout differs between _native.py and the .so")

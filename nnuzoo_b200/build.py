@@ -21,7 +21,7 @@ LIB = os.path.join(LIBDIR, "libnnuzoo_b200.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
 SOURCES = ["capi.cu", "cross_kernels.cu", "conv1d_kernels.cu", "proj_kernels.cu", "norm_kernels.cu", "dwconv_kernels.cu",
-           "epilogue_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", "scan_inst_f16.cu", "scan_rl_inst_f32.cu",
+           "epilogue_kernels.cu", "sw_kernels.cu", "scan_inst_f32.cu", "scan_inst_bf16.cu", "scan_inst_f16.cu", "scan_rl_inst_f32.cu",
            "scan_rl_inst_bf16.cu", "scan_rl_inst_f16.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas=-warn-spills"]

@@ -9,6 +9,11 @@ Mirror of the reference predictor's inner path:
   fp16 accumulators, ``logits += prediction * gaussian``, ``n += gaussian``, final division, inf check
                                                          :567-634
 What is different, by design:
+  * on a CUDA device the whole per-tile arithmetic -- mirror average (:549-565), conversion to the accumulator dtype,
+    gaussian weighting and both accumulations (:617-623) -- is ONE kernel per batch of tiles (``nz_sw_accumulate``,
+    csrc/sw_kernels.cu) instead of ~3 + 2 * mirrors element-wise launches per tile; it rounds after every step exactly
+    as the PyTorch expressions do, so the accumulators are bit-identical (tests/test_predict_gpu.py).  Overlapping tiles
+    of one batch are issued one by one.  ``fused_accumulate=False`` keeps the eager expressions;
   * ``tile_batch`` tiles go through the network per forward (the reference uses batch 1, :614), and the mirrored
     copies of a batch are stacked into the same forward when ``stack_mirrors`` -- an eval-mode network treats samples
     independently, so the per-tile results are the same numbers;
@@ -26,6 +31,9 @@ from typing import List, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+_SW_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 
 def _gauss_1d(n: int, sigma: float, truncate: float = 4.0) -> torch.Tensor:
@@ -116,7 +124,7 @@ class SlidingWindowPredictor:
     def __init__(self, network: torch.nn.Module, patch_size: Sequence[int], num_heads: int, device,
                  tile_step_size: float = 0.5, use_gaussian: bool = True, use_mirroring: bool = True,
                  mirror_axes: Sequence[int] | None = None, tile_batch: int = 4, stack_mirrors: bool = True,
-                 autocast_dtype=torch.float16, results_dtype=torch.float16):
+                 autocast_dtype=torch.float16, results_dtype=torch.float16, fused_accumulate: bool = True):
         self.device = torch.device(device)
         self.network = network.to(self.device).eval()
         self.patch_size = tuple(int(p) for p in patch_size)
@@ -129,7 +137,72 @@ class SlidingWindowPredictor:
         self.stack_mirrors = stack_mirrors
         self.autocast_dtype = autocast_dtype
         self.results_dtype = results_dtype
+        self.fused_accumulate = fused_accumulate
         self.forwards = 0   # network invocations of the last call (for the bench)
+
+    # -- mirror average + gaussian multiply-accumulate of a batch of tiles as one kernel ----------------------------
+    def _combos(self):
+        return [c for i in range(len(self.mirror_axes))
+                for c in itertools.combinations([m + 2 for m in self.mirror_axes], i + 1)]
+
+    def _can_fuse(self, data) -> bool:
+        return (self.fused_accumulate and self.device.type == "cuda" and self.stack_mirrors
+                and self.results_dtype in _SW_DT and data.dim() - 1 <= 3 and len(self._combos()) + 1 <= 8)
+
+    def _predict_stacked(self, x: torch.Tensor) -> torch.Tensor:
+        """All mirrored copies of a batch in one forward; returns the raw stacked output (passes, then tiles)."""
+        combos = self._combos()
+        self.forwards += 1
+        if not combos:
+            return self.network(x)
+        return self.network(torch.cat([x] + [torch.flip(x, c) for c in combos], 0))
+
+    def _accumulate_fused(self, out, group, logits, n_pred, gaussian, nd_vol):
+        import ctypes
+
+        from . import _native
+        combos = self._combos()
+        n = len(group)
+        nt = len(self.patch_size)                      # tile axes are the LAST nt axes of the volume
+        lead = nd_vol - nt                             # 2-D tiles walked through a 3-D volume: one leading slice axis
+        pad = 3 - nd_vol
+        tile = [1] * (pad + lead) + list(self.patch_size)
+        vol = [1] * pad + list(logits.shape[1:])
+        offs = []
+        for sl in group:                               # sl = (slice(None), *per-axis slices or ints)
+            o = []
+            for s_ in sl[1:]:
+                o.append(int(s_.start) if isinstance(s_, slice) else int(s_))
+            offs.append([0] * pad + o)
+        masks = [0] + [sum(1 << (pad + lead + (ax - 2)) for ax in c) for c in combos]
+        if out.dtype not in _SW_DT:
+            out = out.float()
+        out = out.contiguous()
+        lib = _native.lib()
+        _native.bind_device(self.device.index)
+        st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        i64 = lambda v: (ctypes.c_int64 * len(v))(*v)  # noqa: E731
+        mk = (ctypes.c_int32 * len(masks))(*masks)
+
+        def launch(first, count):
+            # pass m of tile t sits at m * n + t: a sub-range of tiles needs its own compact stack
+            src = out if count == n else torch.cat([out[m * n + first:m * n + first + count] for m in range(len(masks))], 0)
+            flat = [v for o in offs[first:first + count] for v in o]
+            with torch.cuda.device(self.device):
+                _native.check(lib.nz_sw_accumulate(
+                    ctypes.c_void_p(src.data_ptr()), _SW_DT[src.dtype], len(masks), mk, count, self.num_heads, i64(tile),
+                    ctypes.c_void_p(gaussian.data_ptr()), _SW_DT[self.results_dtype], ctypes.c_void_p(logits.data_ptr()),
+                    ctypes.c_void_p(n_pred.data_ptr()), i64(vol), i64(flat), st), "nz_sw_accumulate")
+
+        def overlap(a, b):
+            return all(a[k] < b[k] + tile[k] and b[k] < a[k] + tile[k] for k in range(3))
+
+        if any(overlap(offs[i], offs[j]) for i in range(n) for j in range(i)):
+            for t in range(n):
+                launch(t, 1)
+        else:
+            for first in range(0, n, 32):
+                launch(first, min(32, n - first))
 
     # -- test-time augmentation (predict_from_raw_data.py:549-565) on a batch of tiles ------------------------------
     def _mirror_and_predict(self, x: torch.Tensor) -> torch.Tensor:
@@ -178,10 +251,14 @@ class SlidingWindowPredictor:
         n_pred = torch.zeros(data.shape[1:], dtype=self.results_dtype, device=dev)
         gaussian = (compute_gaussian(self.patch_size, 1.0 / 8, 10, self.results_dtype, dev) if self.use_gaussian
                     else torch.ones(self.patch_size, dtype=self.results_dtype, device=dev))
+        fuse = self._can_fuse(data)
         with torch.autocast(dev.type, dtype=self.autocast_dtype, enabled=dev.type == "cuda"):
             for i in range(0, len(mine), self.tile_batch):
                 group = mine[i:i + self.tile_batch]
                 batch = torch.stack([data[sl] for sl in group], 0)
+                if fuse:
+                    self._accumulate_fused(self._predict_stacked(batch), group, logits, n_pred, gaussian, data.dim() - 1)
+                    continue
                 pred = self._mirror_and_predict(batch).to(self.results_dtype)
                 if self.use_gaussian:
                     pred *= gaussian
