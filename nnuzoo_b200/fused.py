@@ -176,6 +176,82 @@ class SS2DFoldedFn(torch.autograd.Function):
                 dg.to(gdt) if dg is not None else None, db.to(bdt) if db is not None else None, None, None, None, None)
 
 
+class _CoreCtx:
+    """Stands in for the autograd ctx of SS2DFoldedFn inside SS2DFoldedProjFn."""
+
+    saved_tensors = ()
+    inner = None
+
+    def __init__(self, needs_grad: bool):
+        self.needs_input_grad = (needs_grad,) * 8 + (True, True, False, False, False, False)
+
+    def save_for_backward(self, *tensors):
+        self.saved_tensors = tensors
+
+
+class SS2DFoldedProjFn(torch.autograd.Function):
+    """x_proj -> split -> dt_proj -> SS2DFoldedFn as ONE node (m2net.py:179-182 + :193-221).
+
+    As separate nodes the backward pays, per SS2D, a concatenation of (d dts_low, dB, dC) into d x_dbl (the adjoint of
+    torch.split), casts of the scan's fp32 dB / dC to the operand dtype on their way there, and an addition of the two
+    gradients of xs2 (from the scan and from x_proj).  Inside one node the scan's fp32 dB / dC are written straight into
+    their row-slices of d x_dbl (one converting copy each), d dts_low lands in its slice from the GEMM, and x_proj's input
+    gradient is accumulated onto the scan's du by the GEMM itself (beta = 1).  The projections stay library GEMMs
+    (L is the long, parallel axis); their weight gradients run on nz_proj_wgrad."""
+
+    @staticmethod
+    def forward(ctx, xs2, wx, wdt, As, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype, R, N):
+        from .proj import proj_wgrad  # noqa: F401  (bound late: proj imports nothing from here)
+        bsz, two, D, L = xs2.shape
+        C = R + 2 * N
+        wxc, wdtc = wx.to(xs2.dtype), wdt.to(xs2.dtype)
+        x_dbl = torch.matmul(wxc.unsqueeze(0), xs2)                            # (B, 2, 2C, L): array a -> directions 2a, 2a+1
+        x4 = x_dbl.view(bsz, 4, C, L)
+        dts = torch.matmul(wdtc.unsqueeze(0), x4[:, :, :R])                     # (B, 4, D, L)
+        core = _CoreCtx(any(ctx.needs_input_grad[:6]))
+        out = SS2DFoldedFn.forward(core, xs2, dts, As, x4[:, :, R:R + N], x4[:, :, R + N:], Ds, dt_bias, z, gamma, beta,
+                                   H, W, eps, out_dtype)
+        # the scan's dB / dC stay fp32 until they are copied into d x_dbl (SelectiveScanFn.backward casts to in_dtypes)
+        t = list(core.inner.in_dtypes)
+        t[2] = t[3] = torch.float32
+        core.inner.in_dtypes = tuple(t)
+        ctx.core = core
+        ctx.save_for_backward(xs2, x_dbl, wxc, wdtc)
+        ctx.meta = (R, N, wx.dtype, wdt.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .proj import proj_wgrad
+        xs2, x_dbl, wxc, wdtc = ctx.saved_tensors
+        R, N, t_wx, t_wdt = ctx.meta
+        bsz, two, D, L = xs2.shape
+        C = R + 2 * N
+        du, ddelta, dA, dB, dC, dD, dbias, dz, dg, db, *_ = SS2DFoldedFn.backward(ctx.core, dout)
+        ctx.core = None
+        x4 = x_dbl.view(bsz, 4, C, L)
+        ddelta = ddelta.view(bsz, 4, D, L)
+        dx4 = torch.empty_like(x4)
+        dx4[:, :, :R] = torch.matmul(wdtc.transpose(1, 2).unsqueeze(0), ddelta)  # d dts_low            (m2net.py:182)
+        dx4[:, :, R:R + N].copy_(dB)                                           # fp32 -> operand dtype, in place   (:181)
+        dx4[:, :, R + N:].copy_(dC)
+        d_wdt = proj_wgrad(ddelta, x4[:, :, :R]).to(t_wdt) if ctx.needs_input_grad[2] else None
+        dx_dbl = dx4.view(bsz, 2, 2 * C, L)
+        d_wx = proj_wgrad(dx_dbl, xs2).to(t_wx) if ctx.needs_input_grad[1] else None
+        d_xs2 = None
+        if ctx.needs_input_grad[0]:                                            # du + W_x^T d x_dbl in one GEMM (:179)
+            wT = wxc.transpose(1, 2).unsqueeze(0).expand(bsz, 2, D, 2 * C).reshape(bsz * 2, D, 2 * C)
+            d_xs2 = torch.baddbmm(du.reshape(bsz * 2, D, L), wT, dx_dbl.view(bsz * 2, 2 * C, L)).view(bsz, 2, D, L)
+        return (d_xs2, d_wx, d_wdt, dA, dD, dbias, dz, dg, db, None, None, None, None, None, None)
+
+
+def ss2d_core_folded_proj(xs2, wx, wdt, As, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype, R, N):
+    """xs2 (B, 2, D, L); wx (2, 2 (R + 2N), D): x_proj weights of directions (2a, 2a + 1) stacked per array a; wdt (4, D, R);
+    As / Ds / dt_bias in folded direction order."""
+    return SS2DFoldedProjFn.apply(xs2, wx, wdt, As, Ds, dt_bias, z, gamma, beta, int(H), int(W), float(eps), out_dtype,
+                                  int(R), int(N))
+
+
 def ss2d_core_folded(xs2, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, H, W, eps, out_dtype):
     """xs2 (B, 2, D, L), dts (B, 4, D, L) contiguous, Bs / Cs (B, 4, N, L) views, all in folded direction order."""
     return SS2DFoldedFn.apply(xs2, dts, As, Bs, Cs, Ds, dt_bias, z, gamma, beta, int(H), int(W), float(eps), out_dtype)

@@ -179,7 +179,8 @@ class SlidingWindowPredictor:
             out = out.float()
         out = out.contiguous()
         lib = _native.lib()
-        _native.bind_device(self.device.index)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        _native.bind_device(dev_index)
         st = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         i64 = lambda v: (ctypes.c_int64 * len(v))(*v)  # noqa: E731
         mk = (ctypes.c_int32 * len(masks))(*masks)

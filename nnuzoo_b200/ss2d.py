@@ -18,6 +18,8 @@ Differences are confined to *how* forward_core executes:
 """
 from __future__ import annotations
 
+import os
+
 import math
 
 import torch
@@ -48,6 +50,8 @@ class _CrossScanSSM(nn.Module):
 
     fuse_epilogue = True   # SS2D: run scan -> merge -> out_norm -> gate as one autograd node (nnuzoo_b200.fused)
     fold_directions = True  # ... on the folded direction layout: no flipped copies, the scan walks backwards instead
+    fuse_projections = os.environ.get("NZ_FUSE_PROJ", "0") == "1"  # x_proj / split / dt_proj inside the same node
+    split_in_proj = os.environ.get("NZ_SPLIT_IN_PROJ", "0") == "1"  # SS2D.forward: in_proj as two GEMMs (no chunk / permute copies)
 
     def _init_ssm(self, d_model, d_state, expand, dt_rank, dt_min, dt_max, dt_init, dt_scale, dt_init_floor,
                   bias, dropout, k, factory_kwargs):
@@ -187,15 +191,19 @@ class _CrossScanSSM(nn.Module):
 
         xs2 = cross_scan_pair(x)                                                    # (B, 2, D, L)
         wx = fold(self.x_proj_weight, C, D).reshape(2, 2 * C, D)                    # array a: directions a and a + 2
-        x_dbl = grouped_proj(xs2, wx).view(bsz, 4, C, H * W)                        # folded order, m2net.py:179
-        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                          # :181
-        dts = grouped_proj(dts, fold(self.dt_projs_weight, D, R).reshape(4, D, R))  # :182
-        if dts.dtype != xs2.dtype:
-            return None
+        wdt = fold(self.dt_projs_weight, D, R).reshape(4, D, R)
         As = -torch.exp(fold(self.A_logs.float(), D, N)).reshape(4 * D, N)          # :190
         Ds = fold(self.Ds.float(), D).reshape(-1)
         bias = fold(self.dt_projs_bias.float(), D).reshape(-1)
         out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else xs2.dtype
+        if self.fuse_projections:   # x_proj, split, dt_proj, scan, merge, norm, gate: one node (:179-182, :193-221)
+            return fused.ss2d_core_folded_proj(xs2, wx, wdt, As, Ds, bias, z, self.out_norm.weight, self.out_norm.bias,
+                                               H, W, self.out_norm.eps, out_dtype, R, N)
+        x_dbl = grouped_proj(xs2, wx).view(bsz, 4, C, H * W)                        # folded order, m2net.py:179
+        dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)                          # :181
+        dts = grouped_proj(dts, wdt)                                                # :182
+        if dts.dtype != xs2.dtype:
+            return None
         return fused.ss2d_core_folded(xs2, dts.contiguous(), As, Bs, Cs, Ds, bias, z, self.out_norm.weight,
                                       self.out_norm.bias, H, W, self.out_norm.eps, out_dtype)
 
@@ -225,8 +233,22 @@ class SS2D(_CrossScanSSM):
 
     def forward(self, x: torch.Tensor, **kwargs):
         bsz, H, W, _ = x.shape
-        x, z = self.in_proj(x).chunk(2, dim=-1)                          # m2net.py:211-212
-        x = x.permute(0, 3, 1, 2).contiguous()
+        if x.is_cuda and self.split_in_proj:
+            # m2net.py:211-213 (in_proj, chunk, permute) as two GEMMs on the halves of the weight: the x half comes out
+            # channels-first -- (D, d_model) @ (B, d_model, L) -- which is what the convolution and the scan read, and
+            # the z half channels-last, which is what the gate reads.  No permuted copy forward, and backward neither
+            # the concatenation of (dx, dz) that chunk's adjoint is nor the permute of dx.
+            D = self.d_inner
+            wgt, b = self.in_proj.weight, self.in_proj.bias
+            flat = x.reshape(bsz, H * W, -1)
+            xc = torch.matmul(wgt[:D], flat.transpose(1, 2))              # (B, D, L)
+            if b is not None:
+                xc = xc + b[:D].to(xc.dtype).unsqueeze(-1)
+            z = F.linear(x, wgt[D:], None if b is None else b[D:])        # (B, H, W, D)
+            x = xc.view(bsz, D, H, W)
+        else:
+            x, z = self.in_proj(x).chunk(2, dim=-1)                      # m2net.py:211-212
+            x = x.permute(0, 3, 1, 2).contiguous()
         c = self.conv2d
         if x.is_cuda and c.kernel_size == (3, 3) and c.padding == (1, 1) and c.dilation == (1, 1):
             x = dwconv3x3_silu(x, c.weight, c.bias)                      # :214-215 as one kernel

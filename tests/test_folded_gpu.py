@@ -201,3 +201,31 @@ def test_folded_scan_equals_flipped_copies_at_full_size(shape):
     names = ["out", "du", "ddelta", "dA", "dB", "dC", "dD", "dbias"]
     errs = {n: float((a - r).abs().max() / r.abs().max()) for n, a, r in zip(names, got, ref)}
     assert all(v < 1e-3 for v in errs.values()), errs
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+@pytest.mark.parametrize("cfg", [(16, 32, 32), (64, 16, 16)])
+def test_projections_inside_the_node_equal_separate_nodes(cfg, autocast):
+    """x_proj / split / dt_proj inside the fused node (fused.SS2DFoldedProjFn) against the same ops as separate autograd
+    nodes (m2net.py:179-182): identical forward arithmetic; backward differs only in where dB / dC are rounded to the
+    operand dtype and in the GEMM accumulating onto du."""
+    from nnuzoo_b200.ss2d import SS2D
+    d_model, H, W = cfg
+    torch.manual_seed(d_model + W)
+    m = SS2D(d_model).to(_dev())
+    x = torch.randn(2, H, W, d_model, device=_dev())
+    outs, grads = [], []
+    for fuse in (True, False):
+        m.fuse_projections = fuse
+        m.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = m(xi)
+        y.float().square().mean().backward()
+        outs.append(y.detach().float())
+        grads.append({"x": xi.grad.float(), **{n: p.grad.float().clone() for n, p in m.named_parameters()}})
+    assert torch.equal(outs[0], outs[1])
+    tol = 3e-2 if autocast else 1e-4
+    for k in grads[0]:
+        e = rel_err(grads[0][k].cpu().numpy(), grads[1][k].cpu().numpy())
+        assert e < tol, f"grad {k}: {e}"
