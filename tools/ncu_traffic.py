@@ -51,8 +51,11 @@ def main(path, out=None):
     for i, d in enumerate(order):
         k = d["kernel"]
         kk = k.replace(" ", "")
-        # last template argument of the aggregate kernel: kFwd
-        is_bwd_agg = "scan_rl_agg_kernel" in kk and any(t in kk for t in ("(bool)0>(", "false>(", ",0>("))
+        # template arguments of the aggregate kernel: <T, kHasZ, kFwd, kRevCap>; the backward's passes have kFwd = 0
+        is_bwd_agg = False
+        if "scan_rl_agg_kernel<" in kk:
+            targs = kk.split("scan_rl_agg_kernel<", 1)[1].split(">", 1)[0].split(",")
+            is_bwd_agg = len(targs) >= 3 and targs[2].replace("(bool)", "") in ("0", "false")
         is_bwd_comb = "combine" in k and i > 0 and order[i - 1] in bwd and "agg" in order[i - 1]["kernel"]
         if "scan_bwd" in k or is_bwd_agg or is_bwd_comb:
             bwd.append(d)
