@@ -152,8 +152,9 @@ int64_t nz_scan_fine_bytes(const NzScanDesc* desc);
  * applies, the per-chunk aggregates of its chunk-parallel decomposition. */
 int64_t nz_scan_workspace_bytes_bwd(const NzScanDesc* desc);
 
-/* 1 when nz_scan_bwd on this problem OVERWRITES dB / dC (every element has a single owner tile, so the caller need not
- * zero them), 0 when it accumulates with atomics into caller-zeroed buffers. */
+/* 1 when nz_scan_bwd on this problem OVERWRITES dB / dC (every element has a single owner tile, or the call zero-fills
+ * them itself before it accumulates -- the row-per-lane backward's aggregate pass does that for free), so the caller
+ * need not zero them; 0 when it accumulates with atomics into caller-zeroed buffers. */
 int nz_scan_bwd_overwrites_dbc(const NzScanDesc* desc);
 
 /* Number of NZ_CHUNK-long chunks (second-to-last extent of the checkpoint tensor x). */

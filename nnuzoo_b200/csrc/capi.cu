@@ -411,6 +411,12 @@ static int64_t rl_extra_bytes(const NzScanDesc* d) {
   return 3 * one;
 }
 
+static int bwd_rl_v2() {
+  int v2 = 1;
+  if (const char* e = getenv("NZ_RL_BWD2")) v2 = atoi(e) != 0;  // A/B against the slab version
+  return v2;
+}
+
 template <typename T>
 static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
   RlArgs r;
@@ -455,13 +461,13 @@ static cudaError_t run_bwd_rl(const NzScanDesc* d, cudaStream_t st) {
     r.wide = a32(d->du) && a32(d->ddelta) && (!d->dz || a32(d->dz)) && (L * (int64_t)esize(d->dtype)) % 32 == 0;
     if (getenv("NZ_RL_NOWIDE")) r.wide = 0;
   }
-  r.v2 = 1;
-  if (const char* e = getenv("NZ_RL_BWD2")) r.v2 = atoi(e) != 0;  // A/B against the slab version
+  r.v2 = bwd_rl_v2();
   rl_plan(d, &r.nchunks, &r.tpc, r.v2 ? NZ_RL_BWD2_MINB : 12);
   r.softplus = d->delta_softplus;
   r.rev_mask = d->rev_mask;
   r.u_gdiv = u_gdiv(d);
   r.single = r.nrb == 1;
+  r.zero_dbc = (!r.single && r.nchunks > 1 && !getenv("NZ_RL_NO_ZERO_DBC")) ? 1 : 0;  // nz_scan_bwd_overwrites_dbc() says so
   if (r.nchunks > 1) {
     const int64_t one = (((int64_t)d->batch * d->dim * r.nchunks * NZ_MAX_DSTATE * 4) + 255) & ~(int64_t)255;
     char* base = reinterpret_cast<char*>(d->workspace) + nz_scan_workspace_bytes(d);
@@ -651,7 +657,14 @@ int64_t nz_scan_workspace_bytes_bwd(const NzScanDesc* d) {
 int nz_scan_bwd_overwrites_dbc(const NzScanDesc* d) {
   if (!d || d->ngroups < 1 || d->dim % d->ngroups) return 0;
   const int dpg = d->dim / d->ngroups;
-  if (d->xf && nz::rl_shape_ok(d)) return dpg == 32 ? 1 : 0;
+  if (d->xf && nz::rl_shape_ok(d)) {
+    // one warp owns every dB / dC element (32 rows per group), or the backward's aggregate pass zero-fills them on its
+    // way (several row blocks per group and more than one chunk: RlArgs::zero_dbc)
+    if (dpg == 32) return 1;
+    int nc = 1, tpc = 1;
+    nz::rl_plan(d, &nc, &tpc, nz::bwd_rl_v2() ? NZ_RL_BWD2_MINB : 12);
+    return (nc > 1 && !getenv("NZ_RL_NO_ZERO_DBC")) ? 1 : 0;
+  }
   return dpg <= nz::kBwdRows ? 1 : 0;
 }
 

@@ -70,6 +70,8 @@ struct alignas(64) RlArgs {
                  // directions that walk the same array forwards and backwards share it); 1 = plain
   int wide;      // every fp32 output row / checkpoint run is 32-byte aligned: one 32-byte store per block
   int v2f;       // forward main pass: 1 = pipelined version (scan_fwd_rl2_kernel)
+  int zero_dbc;  // backward, several row blocks per group (dB / dC are reduced with RED): the aggregate pass zero-fills
+                 // dB / dC on its way (its stores are free under the MUFU bound), so the caller need not
 };
 
 // ---- exp2 on the FMA pipe ----
@@ -258,8 +260,22 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
   for (int n = 0; n < kMaxState; ++n) amax = fmaxf(amax, fabsf(A2[n]));
   const float dlim = 126.f / fmaxf(amax, 1e-30f);  // |A2 * dl| <= 126 for the exponent arithmetic of ex2_poly2
 
+  // dB / dC of this (batch, group), zero-filled tile by tile by the warp of row block 0 (kFwd == false only)
+  auto zero_tile = [&](int t) {
+    float* zb = a.dB + (((long)b * a.ngroups + g) * kMaxState) * a.L + (long)t * TB;
+    float* zc = a.dC + (((long)b * a.ngroups + g) * kMaxState) * a.L + (long)t * TB;
+#pragma unroll 4
+    for (int n = 0; n < kMaxState; ++n)
+#pragma unroll
+      for (int j = 0; j < TB; j += 32) {
+        zb[(long)n * a.L + j + lane] = 0.f;
+        zc[(long)n * a.L + j + lane] = 0.f;
+      }
+  };
+  const bool zero_dbc = !kFwd && a.zero_dbc && rb == 0;
   for (int k = 0; k < nt; ++k) {
     const int s = k & 1;
+    if (zero_dbc) zero_tile(tile_of(k));
     mbar_wait(&bars[s], (k >> 1) & 1);
     const uint32_t st = smem_s + s * STAGE;
 #pragma unroll 1
@@ -319,6 +335,11 @@ __global__ void __launch_bounds__(32, 10) scan_rl_agg_kernel(const __grid_consta
     }
     __syncwarp();  // every lane is done with stage s
     if (lane == 0 && k + 2 < nt) issue(tile_of(k + 2), s);
+  }
+  if (zero_dbc) {  // the chunk no work item aggregates (the last in walking order) is zero-filled by its neighbour
+    const int cs = down ? 0 : a.nchunks - 1;
+    if (c == (down ? 1 : a.nchunks - 2))
+      for (int t = cs * a.tpc; t < min(a.ntl, (cs + 1) * a.tpc); ++t) zero_tile(t);
   }
   float* G = a.aggG + (rowg * a.nchunks + c) * kMaxState;
   float* Q = a.aggQ + (rowg * a.nchunks + c) * kMaxState;

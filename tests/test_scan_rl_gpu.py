@@ -107,3 +107,36 @@ def test_inference_does_not_take_fine_checkpoints(monkeypatch):
     peak = torch.cuda.max_memory_allocated() - base
     fine = 2 * 128 * (1024 // 8) * 16 * 4
     assert peak < out.numel() * 4 + fine, "the forward must not have allocated the fine checkpoints"
+
+
+@pytest.mark.parametrize("shape", [(2, 128, 2, 16, 4128, False), (1, 96, 1, 16, 992, True), (2, 256, 2, 16, 2048, False)])
+@pytest.mark.parametrize("items", ["7", "100000"])
+def test_backward_zero_fills_db_dc_itself(shape, items, monkeypatch):
+    """With several row blocks per group the row-per-lane backward accumulates dB / dC with RED; its aggregate pass
+    zero-fills them first (RlArgs::zero_dbc, nz_scan_bwd_overwrites_dbc() == 1), so the caller hands over uninitialised
+    buffers.  Every torch.empty of this test returns NaN-poisoned memory: any element the kernels fail to write or to
+    zero shows up in the comparison with the fp64 oracle."""
+    from nnuzoo_b200 import _native
+    from nnuzoo_b200._native import NzScanDesc
+    monkeypatch.setenv("NZ_RL_MIN_ELTS", "0")
+    monkeypatch.setenv("NZ_RL_ITEMS", items)
+    batch, dim, groups, N, L, has_z = shape
+    d = NzScanDesc()
+    d.batch, d.dim, d.dstate, d.ngroups, d.seqlen, d.dtype = batch, dim, N, groups, L, 0
+    d.u = d.delta = d.B = d.C = ctypes.c_void_p(4096)
+    d.xf = ctypes.c_void_p(4096)
+    for s in (d.u_stride, d.delta_stride):
+        s[0], s[1] = dim * L, L
+    for s in (d.B_stride, d.C_stride):
+        s[0], s[1], s[2] = groups * N * L, N * L, L
+    if items == "100000":  # many chunks: the aggregate pass exists and does the zero fill (one chunk: the caller zeroes)
+        assert _native.lib().nz_scan_bwd_overwrites_dbc(ctypes.byref(d)) == 1
+    orig = torch.empty
+
+    def poisoned(*a, **k):
+        t = orig(*a, **k)
+        return t.fill_(float("nan")) if t.is_floating_point() and t.is_cuda else t
+
+    monkeypatch.setattr(torch, "empty", poisoned)
+    inp, gout = _seeded(batch, dim, groups, N, L, has_z, seed=5 + L)
+    _compare(inp, gout, "float32")
