@@ -20,7 +20,7 @@ training step at BASELINE configs[1]: batch 12 x 1x512x512 (scan list: SURVEY.md
              nnuzoo_b200.train.Trainer (pinned-host batch in, bf16 autocast, Dice+CE deep supervision, backward + DDP
              all-reduce over NCCL, clip, AdamW, loss read back), 12 patches of 1x512x512 per GPU: patches/s.
   infer      BASELINE configs[4]: nnuzoo_b200.predict.SlidingWindowPredictor over a synthetic 1x200x512x512 volume,
-             tiles sharded rank::world, gaussian fp16 accumulators merged with one all-reduce each: volumes/s, slices/s.
+             slices sharded over ranks in contiguous runs, gaussian fp16 accumulators, one all-gather: volumes/s, slices/s.
 
 Multi-GPU (torchrun, one rank per GPU): the scan has no cross-row dependency and the path has no
 exchange step, so every rank runs the full per-GPU batch (weak scaling, "replicas only", no
@@ -721,8 +721,8 @@ def train_run(dev, world, steps, warmup, per_gpu_batch, sync_bn=True, scaling="w
 def infer_run(dev, world, slices, tile_batch):
     """BASELINE configs[4]: sliding-window inference of SS2D2Net over a synthetic (1, slices, 512, 512) volume, 2-D
     tiles of 512x512 (step 0.5), mirroring over both axes (4 forwards per tile, stacked), gaussian-weighted fp16
-    accumulators; tiles sharded ``rank::world`` and merged with one all-reduce per accumulator (strong scaling: one
-    volume whatever N).  Timed: volume already on the device -> merged logits on the device."""
+    accumulators; the 200 disjoint slices are dealt as contiguous balanced runs per rank and merged with one all-gather
+    of the finished slabs (strong scaling: one volume whatever N).  Timed: volume already on the device -> merged logits on the device."""
     import torch
 
     from nnuzoo_b200.m2net import get_m2net
@@ -748,7 +748,9 @@ def infer_run(dev, world, slices, tile_batch):
             "volume": [1, slices, 512, 512], "tile_batch": tile_batch, "forwards_per_rank": pred.forwards,
             "mirroring": "axes (0, 1), 4 passes per tile stacked into one forward", "autocast": "bf16 (random-init weights overflow the reference's fp16 default)",
             "scaling": "strong", "finite": bool(torch.isfinite(out).all()),
-            "merge": "all_reduce(sum) of fp16 logits + weights over NCCL, then divide" if world > 1 else "single rank"}
+            "merge": ("disjoint slices: contiguous balanced runs per rank, divided locally, ONE all_gather of the finished fp16 "
+                      "slabs over NCCL (nnuzoo_b200/predict.py)") if world > 1 else "single rank",
+            "accumulate": "nz_sw_accumulate (mirror average + gaussian multiply-accumulate, one launch per tile batch)"}
 
 
 def run_gpu_arm(args):

@@ -81,12 +81,16 @@ class DiceCELoss(nn.Module):
         intersect = (prob * onehot).sum(axes)
         sum_pred = prob.sum(axes)
         if self.batch_dice:
+            # batch dice: the statistics are summed over the batch -- over this rank's samples first, then over ranks
+            intersect, sum_pred, sum_gt = intersect.sum(0), sum_pred.sum(0), sum_gt.sum(0)
             if self.ddp:
-                # the reference gathers the three statistics one by one (dice.py:107-111); stacked they are one
-                # all-gather (and one all-reduce in the backward) per head instead of three
+                # the reference gathers the three per-sample statistics one by one (dice.py:107-111) and sums afterwards;
+                # that needs the same batch size on every rank, which its own split of a global batch does not give
+                # (12 over 8 ranks = 2,2,2,2,1,1,1,1: nnUNetTrainer.py:420-429).  Summing locally first makes the
+                # gathered tensor (3, classes) on every rank -- the same sum, one all-gather (and one all-reduce in the
+                # backward) per head instead of three, and no dependence on the per-rank batch.
                 packed = torch.stack((intersect, sum_pred, sum_gt.to(sum_pred.dtype)), 0)
                 intersect, sum_pred, sum_gt = _AllGatherWithGrad.apply(packed).sum(0).unbind(0)
-            intersect, sum_pred, sum_gt = intersect.sum(0), sum_pred.sum(0), sum_gt.sum(0)
         dc = (2 * intersect + self.smooth) / torch.clip(sum_gt + sum_pred + self.smooth, 1e-8)
         return ce - dc.mean()
 
@@ -126,6 +130,14 @@ class Trainer:
         network = network.to(self.device)
         self.module = network
         if self.ddp:
+            # 1x1 convolution weights (n, c, 1, 1) receive gradients whose size-1 axes carry channels-last strides; DDP
+            # then warns "Grad strides do not match bucket view strides" and copies every such gradient into its bucket
+            # instead of producing it there.  Normalise the strides where the gradient is born.
+            for prm in network.parameters():
+                if prm.dim() == 4 and tuple(prm.shape[2:]) == (1, 1):
+                    shape, strides = tuple(prm.shape), (prm.shape[1], 1, 1, 1)
+                    prm.register_hook(lambda g, sh=shape, st=strides: g if g.stride() == st else (
+                        g.as_strided(sh, st) if g.stride()[:2] == st[:2] else g.contiguous().as_strided(sh, st)))
             ids = [self.device.index] if self.device.type == "cuda" else None
             # static_graph: the unused 1x1 heads inside every MU (m2net.py:432) are the same every step
             network = nn.parallel.DistributedDataParallel(network, device_ids=ids, static_graph=True,

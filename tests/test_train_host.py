@@ -110,3 +110,38 @@ def test_ddp_step_equals_full_batch_step_gloo():
         tr.train_step(data, tgt[0])
     for k, v in net.state_dict().items():
         assert torch.allclose(v, torch.from_numpy(sd2[k]), atol=2e-6, rtol=1e-4), k
+
+
+def _uneven_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        tr = Trainer(_TinyNet(), "cpu", lr=1e-2)
+        data, tgt = synthetic_batch(4, 1, 3, patch=(16, 16), scales=(1.0,), seed=5, pin=False)
+        sizes = split_global_batch(4, world)          # [2, 1, 1]
+        lo = sum(sizes[:rank])
+        for _ in range(2):
+            loss = tr.train_step(data[lo:lo + sizes[rank]], tgt[0][lo:lo + sizes[rank]])
+        q.put((rank, float(loss), float(sum(p.double().sum() for p in tr.module.parameters()))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_uneven_batch_split_runs_and_keeps_ranks_in_step_gloo():
+    """The reference's own split of a global batch is uneven (12 over 8 ranks = 2,2,2,2,1,1,1,1, nnUNetTrainer.py:420-429).
+    The batch-dice all-gather must not depend on the per-rank batch size (it hung an 8-GPU run when it did): world 3,
+    global batch 4 -> 2, 1, 1 finishes, and every rank ends with the same parameters."""
+    assert split_global_batch(12, 8) == [2, 2, 2, 2, 1, 1, 1, 1]
+    port = 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_uneven_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0, "a rank hung or failed"
+    got = sorted(q.get() for _ in range(3))
+    assert all(abs(g[2] - got[0][2]) < 1e-9 for g in got)
+    assert all(g[1] == g[1] for g in got)   # finite
