@@ -765,7 +765,9 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that cannot complete (a rank gone, mismatched sizes) aborts after 5 minutes instead of NCCL's 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
     from nnuzoo_b200 import _native
 
     wl = Workload(dev)
