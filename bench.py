@@ -111,7 +111,7 @@ def traffic_per_launch():
     try:
         with open(os.path.join(ROOT, "profiles", "r02_bwd_traffic.json")) as f:
             j = json.load(f)
-            return float(j["dram_bytes_per_launch"]), j.get("git")
+            return float(j["dram_bytes_per_launch"]), j.get("git") if not j.get("note") else f'{j.get("git")} ({j["note"]})'
     except Exception:
         return None, None
 
