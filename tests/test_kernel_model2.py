@@ -150,3 +150,43 @@ def test_mirrored_passes_read_back_through_their_own_flip(tile):
             acc = acc + passes[m][fe]
         got[e] = acc / len(passes)
     assert np.allclose(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("pd,rd", [("float16", "float16"), ("bfloat16", "float16"), ("bfloat16", "bfloat16"),
+                                   ("float32", "float32"), ("float16", "float32")])
+def test_rounding_sequence_of_the_accumulate_equals_the_eager_expressions(pd, rd):
+    """sw_accumulate_kernel computes in fp32 and rounds to the prediction dtype after every add and after the division,
+    to the accumulator dtype after the conversion, the gaussian multiply and each accumulate.  That sequence, written out
+    with explicit roundings, must equal the reference's in-place 16-bit tensor expressions
+    (predict_from_raw_data.py:549-565, :617-623) bit for bit."""
+    import torch
+    pdt, rdt = getattr(torch, pd), getattr(torch, rd)
+    g = torch.Generator().manual_seed(0)
+    passes = [torch.randn(3, 5, 7, generator=g).to(pdt) for _ in range(4)]          # already flipped back
+    gauss = (torch.rand(5, 7, generator=g) * 10).to(rdt)
+    logits0 = torch.randn(3, 5, 7, generator=g).to(rdt)
+    n0 = torch.rand(5, 7, generator=g).to(rdt)
+    # eager (the reference's statement)
+    pred = passes[0].clone()
+    for p in passes[1:]:
+        pred += p
+    pred /= len(passes)
+    pred = pred.to(rdt)
+    pred *= gauss
+    logits = logits0.clone()
+    logits += pred
+    n = n0.clone()
+    n += gauss
+    # the kernel's sequence: fp32 arithmetic, one rounding per step
+    rp = lambda t: t.to(pdt).float()  # noqa: E731
+    rr = lambda t: t.to(rdt).float()  # noqa: E731
+    acc = passes[0].float()
+    for p in passes[1:]:
+        acc = rp(acc + p.float())
+    acc = rp(acc * (1.0 / len(passes)))
+    v = rr(acc)
+    v = rr(v * gauss.float())
+    lk = rr(logits0.float() + v).to(rdt)
+    nk = rr(n0.float() + gauss.float()).to(rdt)
+    assert torch.equal(lk, logits) and torch.equal(nk, n)
