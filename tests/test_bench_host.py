@@ -52,3 +52,22 @@ def test_reference_arm_other_ranks_exit_without_work():
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                                   env=env, text=True, timeout=60)
     assert out.strip() == ""
+
+
+def test_exposed_nccl_interval_arithmetic():
+    """tools/prof_ddp.py: EXPOSED NCCL time = length of (union of NCCL kernel intervals) minus (union of compute kernel
+    intervals)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "prof_ddp", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "prof_ddp.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    nccl = m.union([(0, 10), (5, 12), (20, 30), (40, 41)])
+    comp = m.union([(2, 6), (8, 9), (11, 25), (50, 60)])
+    assert nccl == [[0, 12], [20, 30], [40, 41]]
+    assert m.length(nccl) == 23
+    # exposed: [0,2) + [6,8) + [9,11) + [25,30) + [40,41) = 2 + 2 + 2 + 5 + 1
+    assert m.subtract(nccl, comp) == 12
+    assert m.subtract(nccl, []) == 23
+    assert m.subtract([], comp) == 0
