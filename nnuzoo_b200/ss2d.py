@@ -218,12 +218,22 @@ class _CrossScanSSM(nn.Module):
 
 
 class SS2D(_CrossScanSSM):
-    """nnunetv2/nets/m2net.py:39-225.  forward: (B, H, W, d_model) -> (B, H, W, d_model)."""
+    """nnunetv2/nets/m2net.py:39-225.  forward: (B, H, W, d_model) -> (B, H, W, d_model).
 
-    def __init__(self, d_model, d_state=16, d_conv=3, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
+    The same class (identical forward, parameter names and shapes) appears as ``SS2D`` in SwinUMamba.py:90-277
+    (constructor spells ``expand`` as ``ssm_ratio``, takes ``act_layer`` and swallows ``**kwargs``), SwinUMambaD.py:154-340
+    (``**kwargs``) and LightSS2DMambaUNet.py:77-262; their VSSBlocks construct it as ``SS2D(d_model=..., dropout=...,
+    d_state=..., **kwargs)`` (SwinUMamba.py:293).  All of those spellings are accepted here, so one class replaces the four."""
+
+    def __init__(self, d_model=96, d_state=16, d_conv=3, expand=2, dt_rank="auto", dt_min=0.001, dt_max=0.1,
                  dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, dropout=0.0, conv_bias=True, bias=False,
-                 device=None, dtype=None):
+                 device=None, dtype=None, ssm_ratio=None, act_layer=None, **kwargs):
         super().__init__()
+        if ssm_ratio is not None:          # SwinUMamba.py:96 names the expansion factor ssm_ratio
+            expand = ssm_ratio
+        if act_layer is not None and act_layer is not nn.SiLU:
+            raise NotImplementedError("SS2D: the fused convolution / gate kernels implement SiLU (the only activation "
+                                      "nnUZoo constructs it with: SwinUMamba.py:107)")
         fk = {"device": device, "dtype": dtype}
         self.d_conv = d_conv
         self._init_ssm(d_model, d_state, expand, dt_rank, dt_min, dt_max, dt_init, dt_scale, dt_init_floor, bias,

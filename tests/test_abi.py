@@ -137,3 +137,18 @@ def test_mamba_block_loads_the_reference_state_dict():
     assert float(sp.min()) >= 1e-4 - 1e-9 and float(sp.max()) <= 0.1 + 1e-6
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(1, 10, 32))
+
+
+def test_ss2d_accepts_every_reference_constructor_spelling():
+    """m2net.py:40-58, SwinUMamba.py:91-113 (ssm_ratio, act_layer, **kwargs), SwinUMambaD.py:155-174 (**kwargs),
+    LightSS2DMambaUNet.py:78-96 and the VSSBlock call SS2D(d_model=..., dropout=..., d_state=..., **kwargs)."""
+    import torch.nn as nn
+
+    from nnuzoo_b200 import SS2D
+    a = SS2D(d_model=32, dropout=0.0, d_state=16)
+    b = SS2D(d_model=32, ssm_ratio=2, act_layer=nn.SiLU, d_state=16, some_future_kwarg=1)
+    assert {k: tuple(v.shape) for k, v in a.state_dict().items()} == {k: tuple(v.shape) for k, v in b.state_dict().items()}
+    c = SS2D(d_model=32, ssm_ratio=1)
+    assert c.d_inner == 32 and SS2D().d_model == 96
+    with pytest.raises(NotImplementedError):
+        SS2D(d_model=32, act_layer=nn.GELU)
